@@ -1,0 +1,174 @@
+/* islam_pvgo.h — C ABI of the B200-native PVGO back-end (libislam_pvgo.so).
+ *
+ * The reference (sair-lab/iSLAM) has no FFI: its back-end is Python calling PyPose.  The entry points below
+ * are what a maintainer binds (ctypes) to replace, one for one, the reference calls
+ *
+ *   pvgo.py:168        PoseVelGraph(init_nodes, init_vels)            -> islam_pvgo_create / _set_state
+ *   pvgo.py:125-165    information matrices + input staging            -> islam_pvgo_set_problem (4 scalars)
+ *   pvgo.py:26-64      PoseVelGraph.forward (4 residual groups)        -> islam_pvgo_linearize / _get_residuals
+ *   pvgo.py:169-180    pp.optim.LM(...).step + StopOnPlateau loop      -> islam_pvgo_lm_reset / _lm_try / _lm_run
+ *   pvgo.py:67-78,95-111  vo_loss / imu_loss (+ autograd to vo_motions) -> islam_pvgo_vo_loss / _imu_loss
+ *   pvgo.py:114-119    align_to                                        -> islam_pvgo_align
+ *   imu_integrator.py:69-164 + pp.module.IMUPreintegrator.forward      -> islam_imu_preintegrate
+ *   PyPose LieTensor Exp/Log/Inv/Mul/Act (+ left-tangent backward)     -> islam_lie_* (elementwise)
+ *
+ * Conventions
+ *   - All tensor arguments are raw DEVICE pointers to contiguous row-major float32 (or as stated) buffers
+ *     allocated by the caller (PyTorch).  The library owns only its handle and workspace.
+ *   - Every call takes the cudaStream_t to enqueue on (as void*), is asynchronous unless stated, and is
+ *     CUDA-graph capturable except the functions marked "synchronises".
+ *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.
+ *   - Numerical failure of the Cholesky (non-positive pivot / NaN) does not abort: it raises `info` in the
+ *     LM state, and the step is abandoned exactly as PyPose's "Linear solver failed. Breaking..." path.
+ *   - A handle is not thread-safe; use one per host thread / stream.
+ *   - SE3 storage [tx,ty,tz,qx,qy,qz,qw]; tangent order [tau(3), phi(3)]; unknown block per node
+ *     [tau, phi, v] (9); left perturbation X <- Exp(d) X.
+ */
+#ifndef ISLAM_PVGO_H_
+#define ISLAM_PVGO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct islam_pvgo islam_pvgo;
+
+typedef struct islam_pvgo_opts {
+    int32_t band_max;    /* edges with |i-j| above this are loop closures (root separator); default 16 */
+    int32_t leaf_max;    /* poses per leaf front; default 8 */
+    int32_t pivot_max;   /* poses eliminated per front; default 8 */
+    int32_t n_parts;     /* contiguous pose windows (multi-GPU sharding); default 1 */
+    int32_t part;        /* this rank's window in [0, n_parts); default 0 */
+    int32_t reserved[3];
+} islam_pvgo_opts;
+
+typedef struct islam_pvgo_dims {
+    int32_t N, E, M;         /* poses, VO/loop-closure edges, IMU pairs (N-1) */
+    int32_t P;               /* unique off-diagonal 9x9 blocks of J^T W J */
+    int32_t F, levels;       /* fronts, elimination-tree height */
+    int32_t band, root_pivots;
+    int32_t max_rows, max_cols;
+    int32_t n_shared_fronts; /* fronts factored redundantly on every rank (multi-GPU) */
+    int32_t reserved;
+    int64_t L_doubles, U_doubles;
+    int64_t shared_doubles;  /* length of the per-try all-reduce buffer (multi-GPU) */
+    double factor_flops;
+} islam_pvgo_dims;
+
+/* LM / trust-region / scheduler state, resident on the device; mirrors the attributes PyPose keeps on
+ * pp.optim.LM (loss, last, reject_count), strategy.TrustRegion (radius, down, damping) and
+ * scheduler.StopOnPlateau (steps, patience_count, continual).  SURVEY.md A.4. */
+typedef struct islam_lm_state {
+    double loss, last, loss_trial;
+    double damping, radius, down;
+    double diag_scale, quality, denom;
+    double lin_loss;          /* sum r^2 at the last linearisation point */
+    int32_t reject_count, steps_done, tries_total, accepted_last;
+    int32_t need_linearize, continual, patience_count, info;
+    int32_t cur, active, do_lin, chol_fail;
+    int32_t loss_valid, pad0, pad1, pad2;
+} islam_lm_state;
+
+typedef struct islam_lm_params {
+    double radius;            /* TrustRegion(radius=...)  pvgo.py:170 */
+    double lm_min, lm_max;    /* LM(min=1e-4, max=1e32)   pvgo.py:171 */
+    double high, low, up, down, factor, tr_min, tr_max;   /* TrustRegion defaults */
+    int32_t reject;           /* LM(reject=16) */
+    int32_t max_steps;        /* StopOnPlateau(steps=10) */
+    int32_t patience;         /* StopOnPlateau(patience=3) */
+    int32_t use_scheduler;    /* 0: exactly max_steps optimizer.step calls */
+    double decreasing;        /* StopOnPlateau(decreasing=1e-3) */
+} islam_lm_params;
+
+/* ---- lifetime (synchronises; host-side symbolic analysis of the fixed graph structure) ------------- */
+int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const int64_t* links_host /* E x 2 */,
+                      const islam_pvgo_opts* opts /* may be NULL */);
+void islam_pvgo_destroy(islam_pvgo* h);
+int islam_pvgo_get_dims(const islam_pvgo* h, islam_pvgo_dims* out);
+void islam_lm_default_params(islam_lm_params* p);
+
+/* ---- problem data (device pointers, copied into the handle) ---------------------------------------- */
+int islam_pvgo_set_problem(islam_pvgo* h, const float* vo_motions /* E x 7 */, const float* imu_drots /* M x 4 */,
+                           const float* imu_dtrans /* M x 3 */, const float* imu_dvels /* M x 3 */,
+                           const float* dts /* M */, const double info_w[4] /* host: w0^2,w1^2,w2^2,w3^2 */,
+                           void* stream);
+int islam_pvgo_set_state(islam_pvgo* h, const float* nodes /* N x 7 */, const float* vels /* N x 3 */, void* stream);
+int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, void* stream);
+
+/* ---- kernel family 1: residuals, Jacobian blocks, J^T W J / J^T W r ------------------------------- */
+int islam_pvgo_linearize(islam_pvgo* h, void* stream);
+/* residual groups in the reference's return order (pvgo.py:64); any pointer may be NULL */
+int islam_pvgo_get_residuals(islam_pvgo* h, float* pgerr /* E x 6 */, float* adjvelerr /* M x 3 */,
+                             float* imuroterr /* M x 3 */, float* transvelerr /* M x 3 */, void* stream);
+/* block-sparse normal equations (float64): Hd N x 81, Ho P x 81 (rows = lower-indexed node), g N x 9,
+ * pairs P x 2 (int32 lo,hi).  Any pointer may be NULL. */
+int islam_pvgo_get_normal_eq(islam_pvgo* h, double* Hd, double* Ho, double* g, int32_t* pairs, void* stream);
+
+/* ---- kernel family 2: damped multifrontal Cholesky solve (testing hook: one solve at a given scale) - */
+int islam_pvgo_solve(islam_pvgo* h, double diag_scale, double lm_min, double lm_max, double* D /* N x 9 */,
+                     int32_t* info_host /* may be NULL; non-NULL synchronises */, void* stream);
+
+/* ---- LM driver ---------------------------------------------------------------------------------------- */
+int islam_pvgo_lm_reset(islam_pvgo* h, const islam_lm_params* p, void* stream);
+/* one try of optimizer.step (linearise if a new step starts, damp, factor, solve, retract, trial loss,
+ * trust-region update, accept / roll back); no host synchronisation */
+int islam_pvgo_lm_try(islam_pvgo* h, void* stream);
+/* optimizer.step: tries until accepted (synchronises once per try to read the verdict) */
+int islam_pvgo_lm_step(islam_pvgo* h, islam_lm_state* out /* may be NULL */, void* stream);
+/* the whole `while scheduler.continual()` loop of pvgo.py:177-180, control flow on the device;
+ * synchronises once at the end (again only if rejected tries exhausted the speculative budget) */
+int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out /* may be NULL */, void* stream);
+int islam_pvgo_get_lm_state(islam_pvgo* h, islam_lm_state* out, void* stream); /* synchronises */
+/* multi-GPU: a try split around the single all-reduce of the shared (separator) panels */
+int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream);
+int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
+int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
+
+/* ---- outer losses and gauge alignment ------------------------------------------------------------------ */
+/* vo_loss (pvgo.py:67-78) at the current nodes (detached) for arbitrary vo_motions P (E x 7):
+ * trans_loss/rot_loss (E); if grad_* given: d loss_e / d(left tangent of P_e) (E x 6 each) */
+int islam_pvgo_vo_loss(islam_pvgo* h, const float* P, float* trans_loss, float* rot_loss,
+                       float* grad_trans /* nullable */, float* grad_rot /* nullable */, void* stream);
+int islam_pvgo_imu_loss(islam_pvgo* h, float* trans_loss /* M */, float* rot_loss /* M */, void* stream);
+/* align_to (pvgo.py:114-119): nodes <- T X0^-1 nodes, vels <- R_T R0^-1 vels; target: 7 floats on device */
+int islam_pvgo_align(islam_pvgo* h, const float* target, float* nodes_out, float* vels_out, void* stream);
+
+/* ---- IMU pre-integration (imu_integrator.py:69-164 fused with pp.module.IMUPreintegrator.forward) ----- */
+/* S samples; K frames; frame f integrates samples [offsets[f], offsets[f+1]) (offsets: K+1 int32, device).
+ * init: pos(3), rot(4 xyzw), vel(3) on device.  motion_mode 0: world-frame chain; 1: relative deltas.
+ * outputs K x 3 / K x 4 / K x 3 (the caller prepends init in world mode, as imu_integrator.py:86-89). */
+int islam_imu_preintegrate(const float* acc /* S x 3 */, const float* gyro /* S x 3 */, const float* dt /* S */,
+                           int32_t S, const int32_t* offsets, int32_t K, const float* init /* 10 */,
+                           float gravity, int32_t motion_mode, float* pos, float* rot, float* vel,
+                           void* workspace /* islam_imu_workspace_bytes(S,K) */, void* stream);
+int64_t islam_imu_workspace_bytes(int32_t S, int32_t K);
+
+/* ---- elementwise LieTensor maps (forward + left-tangent backward), n elements ------------------------- */
+enum { ISLAM_SE3 = 0, ISLAM_SO3 = 1 };
+int islam_lie_exp(int32_t group, const float* x, float* y, int64_t n, void* stream);          /* algebra -> group */
+int islam_lie_log(int32_t group, const float* x, float* y, int64_t n, void* stream);          /* group -> algebra */
+int islam_lie_inv(int32_t group, const float* x, float* y, int64_t n, void* stream);
+int islam_lie_mul(int32_t group, const float* a, const float* b, float* y, int64_t n, void* stream);
+int islam_lie_act(int32_t group, const float* x, const float* p, float* y, int64_t n, void* stream);
+/* backward: given dL/dy (embedding-sized rows, tangent in the leading slots) produce dL/dx likewise */
+int islam_lie_exp_bwd(int32_t group, const float* x, const float* gy, float* gx, int64_t n, void* stream);
+int islam_lie_log_bwd(int32_t group, const float* y, const float* gy, float* gx, int64_t n, void* stream);
+int islam_lie_inv_bwd(int32_t group, const float* y, const float* gy, float* gx, int64_t n, void* stream);
+int islam_lie_mul_bwd(int32_t group, const float* a, const float* gy, float* ga, float* gb, int64_t n, void* stream);
+int islam_lie_act_bwd(int32_t group, const float* x, const float* p, const float* gy, float* gx, float* gp,
+                      int64_t n, void* stream);
+
+/* ---- host-only introspection of the symbolic analysis (needs no GPU; arrays are int32 except f_Loff/f_Uoff int64) -- */
+typedef struct islam_plan islam_plan;
+int islam_plan_build(islam_plan** out, int32_t N, int32_t E, const int64_t* links_host, const islam_pvgo_opts* opts);
+void islam_plan_free(islam_plan* p);
+int64_t islam_plan_array(const islam_plan* p, const char* name, const void** ptr); /* returns length or -1 */
+
+const char* islam_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLAM_PVGO_H_ */

@@ -1,0 +1,52 @@
+"""Build recipe for libislam_pvgo.so (hand-written CUDA for sm_100a + the C ABI of include/islam_pvgo.h).
+
+    python -m islam_b200.build            # rebuild if any source is newer than the library
+
+nvcc cross-compiles without a GPU; the library is built in-tree (islam_b200/lib/) so it travels to the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'lib', 'libislam_pvgo.so')
+SOURCES = ['pvgo.cu', 'imu.cu', 'lieops.cu', 'symbolic.cpp']
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def _nvcc():
+    for c in (shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError('nvcc not found: libislam_pvgo.so cannot be built')
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'islam_pvgo.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [_nvcc(), '-O3', '-std=c++17', *ARCH, '-lineinfo', '-Xcompiler', '-fPIC', '-shared',
+           '-diag-suppress', '177', '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, '-Xptxas'); cmd.insert(2, '-v')
+        print(' '.join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

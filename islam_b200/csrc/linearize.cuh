@@ -1,0 +1,384 @@
+// Kernel family 1 — per-factor SE(3) residuals + Jacobian blocks and deterministic assembly of the
+// block-sparse normal equations  H = J^T W J (float64 9x9 blocks),  g = J^T W r.
+//
+// Restates /root/reference/pvgo.py:26-64 (PoseVelGraph.forward) together with the Jacobian blocks that
+// PyPose's autograd produces for it and the information weights of pvgo.py:125-129.
+// Residual/Jacobian arithmetic is float32 (the reference's dtype); products and sums that form H and g
+// are float64 because the damped system has cond ~1e8 (DESIGN.md "precision").
+#pragma once
+#include "common.cuh"
+#include "lie.cuh"
+
+namespace islam {
+
+constexpr int LIN_THREADS = 128;
+
+struct ProblemView {
+    int N, E, M;
+    const int* ei;        // [E] first endpoint (pvgo.py:36  nodes[edges[:,0]])
+    const int* ej;        // [E] second endpoint
+    const float* Z;       // [E,7] vo_motions
+    const float* drot;    // [M,4]
+    const float* dtrans;  // [M,3]
+    const float* dvel;    // [M,3]
+    const float* dt;      // [M]
+    const int* edge_owner;  // [E] window that owns the factor (multi-GPU) or nullptr
+    const int* pair_owner;  // [M]
+    int part;
+    double w0, w1, w2, w3;  // information scalars (pvgo.py:125-129)
+};
+
+struct LinBuffers {
+    float* r_vo;     // [E,6]  pgerr
+    float* J_vo;     // [E,18] Mm (3x3) then K (3x3):  J_j = [[Mm, K],[0, Mm]],  J_i = -J_j
+    double* S_vo;    // [E,36] w0 * J^T J
+    double* q_vo;    // [E,6]  w0 * J^T r
+    float* r_imu;    // [M,9]  adjvelerr(3), imuroterr(3), transvelerr(3)
+    float* J_rot;    // [M,9]  Jl^-1(r) dR^T Ri^T
+    double* loss_part;   // [nblk_vo + nblk_imu] partial sums of r^2 (unweighted — PyPose model.loss)
+};
+
+__device__ __forceinline__ void load7(const float* p, float* x) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) x[i] = p[i];
+}
+
+// r = Log(Z^-1 Xi^-1 Xj);  Mm = Jl^-1(phi) R(A),  K = (Jl^-1 [tA]x - Jl^-1 Q Jl^-1) R(A),  A = Z^-1 Xi^-1
+__device__ __forceinline__ void vo_factor(const float* Xi, const float* Xj, const float* Zm, float* r, float* Mm,
+                                          float* K) {
+    float Zi[7], Xii[7], A[7], Eerr[7], Ji[9];
+    se3_inv(Zm, Zi);
+    se3_inv(Xi, Xii);
+    se3_mul(Zi, Xii, A);
+    se3_mul(A, Xj, Eerr);
+    se3_log(Eerr, r, Ji);
+    if (Mm == nullptr) return;
+    float R[9], Q[9], T1[9], T2[9];
+    q_matrix(A + 3, R);
+    mat3_mul(Ji, R, Mm);
+    se3_Q(r, Q);
+    mat3_mul(Ji, Q, T1);
+    mat3_mul(T1, Ji, T2);     // Ji Q Ji
+    float tx[9] = {0, -A[2], A[1], A[2], 0, -A[0], -A[1], A[0], 0};
+    mat3_mul(Ji, tx, T1);     // Ji [t]x
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T1[i] -= T2[i];
+    mat3_mul(T1, R, K);
+}
+
+// r = Log(dR^-1 Ri^-1 Rj);  Jrot = Jl^-1(r) R(dR^-1 Ri^-1)
+__device__ __forceinline__ void rot_factor(const float* qi, const float* qj, const float* dq, float* r, float* Jr) {
+    float a[4], b[4], c[4], e[4];
+    q_inv(dq, a);
+    q_inv(qi, b);
+    q_mul(a, b, c);
+    q_mul(c, qj, e);
+    so3_log(e, r);
+    if (Jr == nullptr) return;
+    float Ji[9], R[9];
+    so3_Jl_inv(r, Ji);
+    q_matrix(c, R);
+    mat3_mul(Ji, R, Jr);
+}
+
+// ---------------------------------------------------------------------------------------------- VO factors
+// mode 0: linearise at the current state (writes r, J, S, q, loss partials)
+// mode 1: trial evaluation — residuals at the trial state (loss partials) and the unweighted
+//         (J D)^T (2 r + J D) term of TrustRegion.update from the stored linearisation
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS)
+k_vo(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+     ProblemView pv, LinBuffers lb, const double* __restrict__ D, double* __restrict__ part_out, int force) {
+    if (!force) {
+        if (!st->active) return;
+        if (MODE == 0 && !st->do_lin) return;
+    }
+    int cur = st->cur;
+    const float* nodes = (MODE == 0) ? (cur ? nodes1 : nodes0) : (cur ? nodes0 : nodes1);
+    __shared__ double sh[LIN_THREADS / 32];
+    __shared__ double sh2[LIN_THREADS / 32];
+    int e = blockIdx.x * LIN_THREADS + threadIdx.x;
+    double lsum = 0.0, qsum = 0.0;
+    bool mine = e < pv.E && (pv.edge_owner == nullptr || pv.edge_owner[e] == pv.part);
+    if (mine) {
+        int i = pv.ei[e], j = pv.ej[e];
+        float Xi[7], Xj[7], Zm[7], r[6];
+        load7(nodes + 7 * (size_t)i, Xi);
+        load7(nodes + 7 * (size_t)j, Xj);
+        load7(pv.Z + 7 * (size_t)e, Zm);
+        if (MODE == 0) {
+            float Mm[9], K[9];
+            vo_factor(Xi, Xj, Zm, r, Mm, K);
+            float* ro = lb.r_vo + 6 * (size_t)e;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ro[k] = r[k];
+            float* Jo = lb.J_vo + 18 * (size_t)e;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { Jo[k] = Mm[k]; Jo[9 + k] = K[k]; }
+            // S = w0 J^T J, q = w0 J^T r with J = [[Mm, K],[0, Mm]]  (float64 products)
+            double J6[6][6];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    J6[a][b] = Mm[3 * a + b]; J6[a][3 + b] = K[3 * a + b];
+                    J6[3 + a][b] = 0.0;       J6[3 + a][3 + b] = Mm[3 * a + b];
+                }
+            double* So = lb.S_vo + 36 * (size_t)e;
+            double* qo = lb.q_vo + 6 * (size_t)e;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double qa = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) qa += J6[k][a] * (double)r[k];
+                qo[a] = pv.w0 * qa;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s += J6[k][a] * J6[k][b];
+                    So[6 * a + b] = pv.w0 * s;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) lsum += (double)r[k] * (double)r[k];
+        } else {
+            vo_factor(Xi, Xj, Zm, r, nullptr, nullptr);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) lsum += (double)r[k] * (double)r[k];
+            // quality term with the linearisation-point J and r
+            const float* Jo = lb.J_vo + 18 * (size_t)e;
+            const float* ro = lb.r_vo + 6 * (size_t)e;
+            double d[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d[k] = D[9 * (size_t)j + k] - D[9 * (size_t)i + k];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double jt = 0.0, jp = 0.0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    jt += (double)Jo[3 * a + b] * d[b] + (double)Jo[9 + 3 * a + b] * d[3 + b];
+                    jp += (double)Jo[3 * a + b] * d[3 + b];
+                }
+                qsum += jt * (2.0 * (double)ro[a] + jt) + jp * (2.0 * (double)ro[3 + a] + jp);
+            }
+        }
+    }
+    double tot = block_sum<LIN_THREADS>(lsum, sh);
+    if (threadIdx.x == 0) part_out[2 * blockIdx.x] = tot;
+    if (MODE == 1) {
+        double tq = block_sum<LIN_THREADS>(qsum, sh2);
+        if (threadIdx.x == 0) part_out[2 * blockIdx.x + 1] = tq;
+    } else if (threadIdx.x == 0) {
+        part_out[2 * blockIdx.x + 1] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- IMU factors
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS)
+k_imu(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+      const float* __restrict__ vels0, const float* __restrict__ vels1, ProblemView pv, LinBuffers lb,
+      const double* __restrict__ D, double* __restrict__ part_out, int force) {
+    if (!force) {
+        if (!st->active) return;
+        if (MODE == 0 && !st->do_lin) return;
+    }
+    int cur = st->cur;
+    const float* nodes = (MODE == 0) ? (cur ? nodes1 : nodes0) : (cur ? nodes0 : nodes1);
+    const float* vels = (MODE == 0) ? (cur ? vels1 : vels0) : (cur ? vels0 : vels1);
+    __shared__ double sh[LIN_THREADS / 32];
+    __shared__ double sh2[LIN_THREADS / 32];
+    int i = blockIdx.x * LIN_THREADS + threadIdx.x;
+    double lsum = 0.0, qsum = 0.0;
+    bool mine = i < pv.M && (pv.pair_owner == nullptr || pv.pair_owner[i] == pv.part);
+    if (mine) {
+        float Xa[7], Xb[7], va[3], vb[3], dq[4], r[9];
+        load7(nodes + 7 * (size_t)i, Xa);
+        load7(nodes + 7 * (size_t)(i + 1), Xb);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { va[k] = vels[3 * (size_t)i + k]; vb[k] = vels[3 * (size_t)(i + 1) + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dq[k] = pv.drot[4 * (size_t)i + k];
+        float dt = pv.dt[i];
+        float Jr[9];
+        rot_factor(Xa + 3, Xb + 3, dq, r + 3, MODE == 0 ? Jr : nullptr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            r[k] = pv.dvel[3 * (size_t)i + k] - (vb[k] - va[k]);                                  // pvgo.py:42
+            r[6 + k] = (Xb[k] - Xa[k]) - (va[k] * dt + pv.dtrans[3 * (size_t)i + k]);             // pvgo.py:51
+        }
+        if (MODE == 0) {
+            float* ro = lb.r_imu + 9 * (size_t)i;
+            float* Jo = lb.J_rot + 9 * (size_t)i;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { ro[k] = r[k]; Jo[k] = Jr[k]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) lsum += (double)r[k] * (double)r[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) lsum += (double)r[k] * (double)r[k];
+            const float* ro = lb.r_imu + 9 * (size_t)i;
+            const float* Jo = lb.J_rot + 9 * (size_t)i;
+            const double* Da = D + 9 * (size_t)i;
+            const double* Db = D + 9 * (size_t)(i + 1);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double j1 = Da[6 + a] - Db[6 + a];                                 // adjvelerr: +I on v_i, -I on v_{i+1}
+                double j2 = 0.0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) j2 += (double)Jo[3 * a + b] * (Db[3 + b] - Da[3 + b]);
+                double j3 = Db[a] - Da[a] - (double)dt * Da[6 + a];                // transvel: [I|0] on tau (A.3 quirk)
+                qsum += j1 * (2.0 * (double)ro[a] + j1) + j2 * (2.0 * (double)ro[3 + a] + j2) +
+                        j3 * (2.0 * (double)ro[6 + a] + j3);
+            }
+        }
+    }
+    double tot = block_sum<LIN_THREADS>(lsum, sh);
+    if (threadIdx.x == 0) part_out[2 * blockIdx.x] = tot;
+    if (MODE == 1) {
+        double tq = block_sum<LIN_THREADS>(qsum, sh2);
+        if (threadIdx.x == 0) part_out[2 * blockIdx.x + 1] = tq;
+    } else if (threadIdx.x == 0) {
+        part_out[2 * blockIdx.x + 1] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- assembly
+struct AsmView {
+    const int* node_eoff;    // CSR node -> incident VO edges
+    const int* node_edges;
+    const int* pair_lo;      // [P]
+    const int* pair_hi;
+    const int* pair_adj;
+    const int* pair_eoff;    // CSR pair -> VO edges
+    const int* pair_edges;
+    int P;
+};
+
+// one warp per node: Hd[n] (9x9, full symmetric) and g[n] (9).  Fixed summation order => deterministic.
+__global__ void __launch_bounds__(128)
+k_assemble_nodes(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Hd,
+                 double* __restrict__ g, int force) {
+    if (!force && !(st->active && st->do_lin)) return;
+    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (n >= pv.N) return;
+    int e0 = av.node_eoff[n], e1 = av.node_eoff[n + 1];
+    bool has_prev = n > 0 && (pv.pair_owner == nullptr || pv.pair_owner[n - 1] == pv.part);
+    bool has_next = n < pv.M && (pv.pair_owner == nullptr || pv.pair_owner[n] == pv.part);
+    const float* Jp = lb.J_rot + 9 * (size_t)(n - 1);
+    const float* Jn = lb.J_rot + 9 * (size_t)n;
+    double dtn = has_next ? (double)pv.dt[n] : 0.0;
+    for (int idx = lane; idx < 81; idx += 32) {
+        int a = idx / 9, b = idx - 9 * a;
+        double v = 0.0;
+        if (a < 6 && b < 6) {
+            for (int k = e0; k < e1; ++k) {
+                int e = av.node_edges[k];
+                if (pv.edge_owner != nullptr && pv.edge_owner[e] != pv.part) continue;
+                v += lb.S_vo[36 * (size_t)e + 6 * a + b];
+            }
+        }
+        if (a >= 3 && a < 6 && b >= 3 && b < 6) {        // imu rotation: w2 Jrot^T Jrot on phi of both ends
+            int aa = a - 3, bb = b - 3;
+            if (has_prev) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += (double)Jp[3 * k + aa] * (double)Jp[3 * k + bb];
+                v += pv.w2 * s;
+            }
+            if (has_next) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += (double)Jn[3 * k + aa] * (double)Jn[3 * k + bb];
+                v += pv.w2 * s;
+            }
+        }
+        if (a == b) {
+            if (a < 3) v += (has_prev ? pv.w3 : 0.0) + (has_next ? pv.w3 : 0.0);               // transvel tau
+            if (a >= 6) v += (has_prev ? pv.w1 : 0.0) + (has_next ? pv.w1 + pv.w3 * dtn * dtn : 0.0);
+        }
+        if (has_next && ((a < 3 && b == a + 6) || (b < 3 && a == b + 6))) v += pv.w3 * dtn;   // tau_i - v_i cross
+        Hd[81 * (size_t)n + idx] = v;
+    }
+    if (lane < 9) {
+        int a = lane;
+        double v = 0.0;
+        if (a < 6) {
+            for (int k = e0; k < e1; ++k) {
+                int e = av.node_edges[k];
+                if (pv.edge_owner != nullptr && pv.edge_owner[e] != pv.part) continue;
+                double q = lb.q_vo[6 * (size_t)e + a];
+                v += (pv.ej[e] == n) ? q : -q;
+            }
+        }
+        const float* rp = lb.r_imu + 9 * (size_t)(n - 1);
+        const float* rn = lb.r_imu + 9 * (size_t)n;
+        if (a < 3) {
+            if (has_prev) v += pv.w3 * (double)rp[6 + a];
+            if (has_next) v -= pv.w3 * (double)rn[6 + a];
+        } else if (a < 6) {
+            int aa = a - 3;
+            if (has_prev) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += (double)Jp[3 * k + aa] * (double)rp[3 + k];
+                v += pv.w2 * s;
+            }
+            if (has_next) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += (double)Jn[3 * k + aa] * (double)rn[3 + k];
+                v -= pv.w2 * s;
+            }
+        } else {
+            int aa = a - 6;
+            if (has_prev) v -= pv.w1 * (double)rp[aa];
+            if (has_next) v += pv.w1 * (double)rn[aa] - pv.w3 * dtn * (double)rn[6 + aa];
+        }
+        g[9 * (size_t)n + a] = v;
+    }
+}
+
+// one warp per unique pair (lo < hi): Ho[p] = H[lo dofs, hi dofs]
+__global__ void __launch_bounds__(128)
+k_assemble_pairs(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Ho,
+                 int force) {
+    if (!force && !(st->active && st->do_lin)) return;
+    int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= av.P) return;
+    int lo = av.pair_lo[p];
+    int e0 = av.pair_eoff[p], e1 = av.pair_eoff[p + 1];
+    bool adj = av.pair_adj[p] && (pv.pair_owner == nullptr || pv.pair_owner[lo] == pv.part);
+    const float* Jr = lb.J_rot + 9 * (size_t)lo;
+    double dt = adj ? (double)pv.dt[lo] : 0.0;
+    for (int idx = lane; idx < 81; idx += 32) {
+        int a = idx / 9, b = idx - 9 * a;
+        double v = 0.0;
+        if (a < 6 && b < 6) {
+            for (int k = e0; k < e1; ++k) {
+                int e = av.pair_edges[k];
+                if (pv.edge_owner != nullptr && pv.edge_owner[e] != pv.part) continue;
+                v -= lb.S_vo[36 * (size_t)e + 6 * a + b];        // S symmetric: same block for (i,j) and (j,i) edges
+            }
+        }
+        if (adj) {
+            if (a >= 3 && a < 6 && b >= 3 && b < 6) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += (double)Jr[3 * k + a - 3] * (double)Jr[3 * k + b - 3];
+                v -= pv.w2 * s;
+            }
+            if (a == b) {
+                if (a < 3) v -= pv.w3;
+                if (a >= 6) v -= pv.w1;
+            }
+            if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w3 * dt;   // (v_lo, tau_hi)
+        }
+        Ho[81 * (size_t)p + idx] = v;
+    }
+}
+
+}  // namespace islam

@@ -1,0 +1,122 @@
+// Device-resident Levenberg-Marquardt controller: trust-region damping, accept / roll back, plateau scheduler.
+// Restates pp.optim.LM.step + strategy.TrustRegion.update + scheduler.StopOnPlateau.step as configured at
+// /root/reference/pvgo.py:169-180 with the control flow kept on the GPU: every kernel of a
+// "try" is predicated on LMState flags, so the host never has to wait for a verdict between tries.
+#pragma once
+#include "common.cuh"
+#include "lie.cuh"
+
+namespace islam {
+
+__global__ void k_begin_try(LMState* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!st->continual) { st->active = 0; return; }
+    st->active = 1;
+    st->do_lin = st->need_linearize;
+    st->chol_fail = 0;
+    st->tries_total += 1;
+}
+
+// sums the partials of the linearisation pass (fixed order) and opens the step / the try
+__global__ void __launch_bounds__(256) k_begin_step(LMState* st, const double* __restrict__ part, int nparts) {
+    if (!st->active) return;
+    __shared__ double sh[8];
+    if (st->do_lin) {
+        double s = 0.0;
+        for (int k = threadIdx.x; k < nparts; k += 256) s += part[2 * k];
+        s = block_sum<256>(s, sh);
+        if (threadIdx.x == 0) {
+            st->lin_loss = s;
+            if (!st->loss_valid) { st->loss = s; st->loss_valid = 1; }     // first call: loss = model.loss()
+            st->last = st->loss;
+            st->reject_count = 0;
+            st->diag_scale = 1.0;
+        }
+    }
+    if (threadIdx.x == 0) st->diag_scale *= (1.0 + st->damping);          // A.diag += A.diag * damping
+}
+
+// nodes <- Exp(d[:6]) nodes ; vels <- vels + d[6:9]   (LieTensor.add_ / update_parameter, A.1/A.4)
+__global__ void __launch_bounds__(128)
+k_retract(const LMState* __restrict__ st, float* nodes0, float* nodes1, float* vels0, float* vels1,
+          const double* __restrict__ D, int N) {
+    if (!st->active) return;
+    int cur = st->cur;
+    const float* ns = cur ? nodes1 : nodes0;
+    float* nd = cur ? nodes0 : nodes1;
+    const float* vs = cur ? vels1 : vels0;
+    float* vd = cur ? vels0 : vels1;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double xi[6], X[7], E[7], O[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi[k] = D[9 * (size_t)n + k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) X[k] = (double)ns[7 * (size_t)n + k];
+    se3_exp(xi, E);
+    se3_mul(E, X, O);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) nd[7 * (size_t)n + k] = (float)O[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vd[3 * (size_t)n + k] = (float)((double)vs[3 * (size_t)n + k] + D[9 * (size_t)n + 6 + k]);
+}
+
+__device__ __forceinline__ void lm_end_step(LMState* st, const islam_lm_params& p) {
+    st->need_linearize = 1;
+    st->steps_done += 1;
+    if (st->steps_done >= p.max_steps) st->continual = 0;
+    if (p.use_scheduler) {                                   // StopOnPlateau.step (A.4)
+        if ((st->last - st->loss) < p.decreasing) st->patience_count += 1;
+        else st->patience_count = 0;
+        if (st->patience_count >= p.patience) st->continual = 0;
+        if (st->reject_count >= p.reject) st->continual = 0;
+    }
+}
+
+// trial loss + trust-region update + accept / roll back
+__global__ void __launch_bounds__(256)
+k_lm_control(LMState* st, islam_lm_params p, const double* __restrict__ part, int nparts) {
+    if (!st->active) return;
+    __shared__ double sh[8], sh2[8];
+    double s = 0.0, q = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
+    s = block_sum<256>(s, sh);
+    q = block_sum<256>(q, sh2);
+    if (threadIdx.x != 0) return;
+    st->loss_trial = s;
+    if (st->chol_fail) {            // "Linear solver failed. Breaking optimization step..." : params untouched
+        st->info = 1;
+        st->loss = st->last;
+        st->accepted_last = 0;
+        lm_end_step(st, p);
+        return;
+    }
+    const double last = st->last, loss = s;
+    const double denom = -q;                                  // -((J D)^T (2 R + J D)), unweighted
+    const double quality = (last - loss) / denom;
+    st->denom = denom;
+    st->quality = quality;
+    double radius = 1.0 / st->damping, down = st->down;
+    if (quality > p.high) { radius *= p.up; down = p.down; }
+    else if (quality > p.low) { down = p.down; }
+    else { radius *= down; down *= p.factor; }
+    down = fmax(p.tr_min, fmin(down, p.tr_max));
+    radius = fmax(p.tr_min, fmin(radius, p.tr_max));
+    st->down = down;
+    st->radius = radius;
+    st->damping = 1.0 / radius;
+    if (last < loss && st->reject_count < p.reject) {        // reject: roll back (the trial buffer is dropped)
+        st->loss = last;
+        st->reject_count += 1;
+        st->need_linearize = 0;
+        st->accepted_last = 0;
+    } else {                                                  // accept: the trial buffer becomes the state
+        st->cur ^= 1;
+        st->loss = loss;
+        st->accepted_last = 1;
+        lm_end_step(st, p);
+    }
+}
+
+// ---- outer losses (pvgo.py:67-78, 95-111) and gauge alignment (pvgo.py:114-119) -----------------------------
+}  // namespace islam

@@ -1,0 +1,735 @@
+// libislam_pvgo.so — handle, workspace and C ABI of the PVGO back-end (see include/islam_pvgo.h).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "lie.cuh"
+#include "linearize.cuh"
+#include "lm.cuh"
+#include "solver.cuh"
+#include "symbolic.h"
+
+using namespace islam;
+
+#define CK(x)                                                     \
+    do {                                                          \
+        cudaError_t _e = (x);                                     \
+        if (_e != cudaSuccess) return (int)_e;                    \
+    } while (0)
+
+namespace {
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        if (count == 0) { p = nullptr; return cudaSuccess; }
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// ---- outer losses / alignment kernels -----------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_vo_loss(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+          const int* __restrict__ ei, const int* __restrict__ ej, const float* __restrict__ P, int E,
+          float* __restrict__ tl, float* __restrict__ rl, float* __restrict__ gt, float* __restrict__ gr) {
+    const float* nodes = st->cur ? nodes1 : nodes0;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float Xi[7], Xj[7], Pm[7], r[6], Mm[9], K[9];
+    load7(nodes + 7 * (size_t)ei[e], Xi);
+    load7(nodes + 7 * (size_t)ej[e], Xj);
+    load7(P + 7 * (size_t)e, Pm);
+    // e = Log(P^-1 n1^-1 n2);  de/d(delta_P) = -Jl^-1(e) Ad(P^-1)   (SURVEY.md A.3 last row)
+    // Jl^-1(e) Ad(A) with A = P^-1 n1^-1 is what vo_factor returns; Ad(P^-1) = Ad(A) Ad(n1), so evaluate it
+    // with Xi = identity-composed form: J_P = Jl^-1(e) Ad(P^-1).
+    float Idn[7] = {0, 0, 0, 0, 0, 0, 1};
+    float C[7], Xii[7];
+    se3_inv(Xi, Xii);
+    se3_mul(Xii, Xj, C);                 // n1^-1 n2
+    vo_factor(Idn, C, Pm, r, Mm, K);     // Log(P^-1 I^-1 C), Jl^-1(e) Ad(P^-1)
+    tl[e] = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    rl[e] = r[3] * r[3] + r[4] * r[4] + r[5] * r[5];
+    if (gt != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                a += Mm[3 * q + k] * r[q];       // Mm^T e_tau
+                b += K[3 * q + k] * r[q];        // K^T  e_tau
+                c += Mm[3 * q + k] * r[3 + q];   // Mm^T e_phi
+            }
+            gt[6 * (size_t)e + k] = -2.f * a;
+            gt[6 * (size_t)e + 3 + k] = -2.f * b;
+            gr[6 * (size_t)e + k] = 0.f;
+            gr[6 * (size_t)e + 3 + k] = -2.f * c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_imu_loss(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+           const float* __restrict__ vels0, const float* __restrict__ vels1, const float* __restrict__ drot,
+           const float* __restrict__ dvel, int M, float* __restrict__ tl, float* __restrict__ rl) {
+    const float* nodes = st->cur ? nodes1 : nodes0;
+    const float* vels = st->cur ? vels1 : vels0;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float r[3], dq[4], qa[4], qb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dq[k] = drot[4 * (size_t)i + k]; qa[k] = nodes[7 * (size_t)i + 3 + k]; qb[k] = nodes[7 * (size_t)(i + 1) + 3 + k]; }
+    rot_factor(qa, qb, dq, r, nullptr);
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = dvel[3 * (size_t)i + k] - (vels[3 * (size_t)(i + 1) + k] - vels[3 * (size_t)i + k]);
+        t += a * a;
+    }
+    tl[i] = t;
+    rl[i] = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+}
+
+__global__ void __launch_bounds__(128)
+k_align(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+        const float* __restrict__ vels0, const float* __restrict__ vels1, const float* __restrict__ target, int N,
+        float* __restrict__ nout, float* __restrict__ vout) {
+    const float* nodes = st->cur ? nodes1 : nodes0;
+    const float* vels = st->cur ? vels1 : vels0;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float X0[7], Tg[7], X0i[7], T[7], X[7], O[7], q0i[4], qr[4], v[3], vo[3];
+    load7(nodes, X0);
+    load7(target, Tg);
+    se3_inv(X0, X0i);
+    se3_mul(Tg, X0i, T);                       // target @ source.Inv()
+    load7(nodes + 7 * (size_t)n, X);
+    se3_mul(T, X, O);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) nout[7 * (size_t)n + k] = O[k];
+    q_inv(X0 + 3, q0i);
+    q_mul(Tg + 3, q0i, qr);                    // target.rotation() @ source.rotation().Inv()
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = vels[3 * (size_t)n + k];
+    q_rot(qr, v, vo);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vout[3 * (size_t)n + k] = vo[k];
+}
+
+__global__ void k_transpose_imu_res(const float* __restrict__ r_imu, int M, float* a, float* b, float* c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (a) a[3 * (size_t)i + k] = r_imu[9 * (size_t)i + k];
+        if (b) b[3 * (size_t)i + k] = r_imu[9 * (size_t)i + 3 + k];
+        if (c) c[3 * (size_t)i + k] = r_imu[9 * (size_t)i + 6 + k];
+    }
+}
+
+__global__ void k_set_state_flags(LMState* st, int cur) {
+    st->cur = cur;
+    st->need_linearize = 1;
+    st->loss_valid = 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+struct islam_pvgo {
+    Plan plan;
+    islam_pvgo_opts opts;
+    islam_lm_params prm;
+    ProblemView pv;
+    LinBuffers lb;
+    AsmView av;
+    FrontMeta fm;
+    // problem + state
+    DevBuf<int> ei, ej, edge_owner, pair_owner;
+    DevBuf<float> Z, drot, dtrans, dvel, dt;
+    DevBuf<float> nodes[2], vels[2];
+    // linearisation
+    DevBuf<float> r_vo, J_vo, r_imu, J_rot;
+    DevBuf<double> S_vo, q_vo, lin_part, trial_part;
+    DevBuf<double> Hd, Ho, g, D;
+    // symbolic plan on the device
+    DevBuf<int> d_node_eoff, d_node_edges, d_pair_lo, d_pair_hi, d_pair_adj, d_pair_eoff, d_pair_edges;
+    DevBuf<int> d_np, d_nb, d_nodes_off, d_nodes, d_child_off, d_children, d_cinv_off, d_cinv, d_hmap_off, d_hmap,
+        d_part, d_level_fronts, d_shared_fronts;
+    DevBuf<long long> d_Loff, d_Uoff, d_shared_off;
+    DevBuf<double> Lbuf, Ubuf, shared;
+    DevBuf<LMState> st;
+    LMState* st_host = nullptr;     // pinned mirror
+    int nblk_vo = 0, nblk_imu = 0;
+    int max_smem_doubles = 0;
+    std::vector<int> level_smem_doubles, level_bs_bytes;
+    // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
+    std::vector<int> level_nlocal;
+    std::vector<long long> h_shared_off;
+    long long shared_doubles = 0;
+    int n_shared = 0;
+    cudaGraphExec_t graph_try = nullptr;
+    cudaStream_t graph_stream = nullptr;
+
+    ~islam_pvgo() {
+        if (graph_try) cudaGraphExecDestroy(graph_try);
+        if (st_host) cudaFreeHost(st_host);
+        DevBuf<int>* ib[] = {&ei, &ej, &edge_owner, &pair_owner, &d_node_eoff, &d_node_edges, &d_pair_lo, &d_pair_hi,
+                             &d_pair_adj, &d_pair_eoff, &d_pair_edges, &d_np, &d_nb, &d_nodes_off, &d_nodes,
+                             &d_child_off, &d_children, &d_cinv_off, &d_cinv, &d_hmap_off, &d_hmap, &d_part,
+                             &d_level_fronts, &d_shared_fronts};
+        for (auto* b : ib) b->release();
+        DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
+                               &r_imu, &J_rot};
+        for (auto* b : fb) b->release();
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &shared};
+        for (auto* b : db) b->release();
+        d_Loff.release(); d_Uoff.release(); d_shared_off.release();
+        st.release();
+    }
+};
+
+extern "C" const char* islam_version(void) { return "islam_b200 0.1.0 (sm_100a)"; }
+
+extern "C" void islam_lm_default_params(islam_lm_params* p) {
+    if (!p) return;
+    p->radius = 1e4;                       // pvgo.py:170  TrustRegion(radius=1e4) (run_pvgo default / train.py:260)
+    p->lm_min = 1e-4; p->lm_max = 1e32;    // pvgo.py:171  LM(min=1e-4)
+    p->high = 0.5; p->low = 1e-3; p->up = 2.0; p->down = 0.5; p->factor = 0.5; p->tr_min = 1e-6; p->tr_max = 1e16;
+    p->reject = 16;
+    p->max_steps = 10; p->patience = 3; p->use_scheduler = 1; p->decreasing = 1e-3;   // pvgo.py:172
+}
+
+extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const int64_t* links, const islam_pvgo_opts* o) {
+    if (!out || N < 2 || E < 0 || (E > 0 && !links)) return -1;
+    islam_pvgo* h = new (std::nothrow) islam_pvgo();
+    if (!h) return -1;
+    islam_pvgo_opts opts;
+    std::memset(&opts, 0, sizeof(opts));
+    if (o) opts = *o;
+    if (opts.band_max <= 0) opts.band_max = 16;
+    if (opts.leaf_max <= 0) opts.leaf_max = 8;
+    if (opts.pivot_max <= 0) opts.pivot_max = 8;
+    if (opts.n_parts <= 0) opts.n_parts = 1;
+    if (opts.part < 0 || opts.part >= opts.n_parts) { delete h; return -1; }
+    h->opts = opts;
+    SymbolicOpts so;
+    so.band_max = opts.band_max; so.leaf_max = opts.leaf_max; so.pivot_max = opts.pivot_max; so.n_parts = opts.n_parts;
+    int rc = build_plan(N, E, links, so, h->plan);
+    if (rc != 0) { delete h; return rc; }
+    Plan& p = h->plan;
+    islam_lm_default_params(&h->prm);
+
+#define UP(buf, vec) do { cudaError_t _e = h->buf.upload(vec); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
+#define AL(buf, cnt) do { cudaError_t _e = h->buf.alloc(cnt); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
+    // edges
+    {
+        std::vector<int> ei(E), ej(E);
+        for (int e = 0; e < E; ++e) { ei[e] = (int)links[2 * e]; ej[e] = (int)links[2 * e + 1]; }
+        UP(ei, ei); UP(ej, ej);
+        if (opts.n_parts > 1) {
+            // a factor is owned by the window holding one of its private endpoints; all-shared factors by window 0
+            std::vector<int> node_part(N);
+            for (int n = 0; n < N; ++n) node_part[n] = p.f_part[p.node_front[n]];
+            std::vector<int> eo(E), po(p.M);
+            for (int e = 0; e < E; ++e) {
+                int a = node_part[ei[e]], b = node_part[ej[e]];
+                eo[e] = a >= 0 ? a : (b >= 0 ? b : 0);
+            }
+            for (int i = 0; i < p.M; ++i) {
+                int a = node_part[i], b = node_part[i + 1];
+                po[i] = a >= 0 ? a : (b >= 0 ? b : 0);
+            }
+            UP(edge_owner, eo); UP(pair_owner, po);
+        }
+    }
+    AL(Z, 7 * (size_t)E); AL(drot, 4 * (size_t)p.M); AL(dtrans, 3 * (size_t)p.M); AL(dvel, 3 * (size_t)p.M); AL(dt, p.M);
+    for (int k = 0; k < 2; ++k) { AL(nodes[k], 7 * (size_t)N); AL(vels[k], 3 * (size_t)N); }
+    AL(r_vo, 6 * (size_t)E); AL(J_vo, 18 * (size_t)E); AL(r_imu, 9 * (size_t)p.M); AL(J_rot, 9 * (size_t)p.M);
+    AL(S_vo, 36 * (size_t)E); AL(q_vo, 6 * (size_t)E);
+    h->nblk_vo = (E + LIN_THREADS - 1) / LIN_THREADS;
+    h->nblk_imu = (p.M + LIN_THREADS - 1) / LIN_THREADS;
+    AL(lin_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu)); AL(trial_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu));
+    AL(Hd, 81 * (size_t)N); AL(Ho, 81 * (size_t)p.P); AL(g, 9 * (size_t)N); AL(D, 9 * (size_t)N);
+    UP(d_node_eoff, p.node_eoff); UP(d_node_edges, p.node_edges); UP(d_pair_lo, p.pair_lo); UP(d_pair_hi, p.pair_hi);
+    UP(d_pair_adj, p.pair_adj); UP(d_pair_eoff, p.pair_eoff); UP(d_pair_edges, p.pair_edges);
+    UP(d_np, p.f_np); UP(d_nb, p.f_nb); UP(d_nodes_off, p.f_nodes_off); UP(d_nodes, p.f_nodes);
+    UP(d_child_off, p.f_child_off); UP(d_children, p.f_children); UP(d_cinv_off, p.c_inv_off); UP(d_cinv, p.c_inv);
+    UP(d_hmap_off, p.f_hmap_off); UP(d_hmap, p.hmap); UP(d_part, p.f_part);
+    UP(d_Loff, p.f_Loff); UP(d_Uoff, p.f_Uoff);
+    // level lists: local fronts first, shared fronts last (multi-GPU: local = fronts of this rank's window)
+    {
+        std::vector<int> lf = p.level_fronts;
+        h->level_nlocal.assign(p.n_levels, 0);
+        h->h_shared_off.assign(p.F, -1);
+        std::vector<int> shared_list;
+        for (int l = 0; l < p.n_levels; ++l) {
+            int b = p.level_off[l], e = p.level_off[l + 1];
+            std::vector<int> loc, shr;
+            for (int k = b; k < e; ++k) {
+                int f = p.level_fronts[k];
+                if (opts.n_parts > 1 && p.f_part[f] < 0) shr.push_back(f);
+                else if (opts.n_parts == 1 || p.f_part[f] == opts.part) loc.push_back(f);
+            }
+            h->level_nlocal[l] = (int)loc.size();
+            // fronts of other windows are dropped from the schedule: keep slots but never launch them
+            int k = b;
+            for (int f : loc) lf[k++] = f;
+            for (int f : shr) { lf[k++] = f; shared_list.push_back(f); }
+            for (; k < e; ++k) lf[k] = -1;
+        }
+        long long off = 0;
+        for (int f : shared_list) {
+            long long Rf = 9LL * (p.f_np[f] + p.f_nb[f]) + 1;
+            h->h_shared_off[f] = off;
+            off += Rf * Rf + 9LL * p.f_np[f];
+        }
+        h->n_shared = (int)shared_list.size();
+        h->shared_doubles = off + 4;      // + [lin loss, trial loss, quality, spare]
+        UP(d_level_fronts, lf);
+        UP(d_shared_fronts, shared_list);
+        UP(d_shared_off, h->h_shared_off);
+        AL(shared, (size_t)h->shared_doubles);
+        cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
+    }
+    AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles);
+    AL(st, 1);
+    if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
+#undef UP
+#undef AL
+    // shared-memory budgets
+    int dev = 0, max_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (max_optin <= 0) max_optin = 227 * 1024;
+    h->max_smem_doubles = (max_optin - 1024) / 8;
+    cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
+    cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
+    h->level_smem_doubles.assign(p.n_levels, 96);
+    h->level_bs_bytes.assign(p.n_levels, 0);
+    for (int f = 0; f < p.F; ++f) {
+        int l = p.f_level[f];
+        long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
+        long long need = Rf * Cf + 96;
+        if (need <= h->max_smem_doubles && need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;
+        long long bs = (Rb + Cf + Cf * (Cf + 1)) * 8;
+        if (bs > max_optin - 1024) { delete h; return -5; }       // boundary too wide for the back-substitution kernel
+        if (bs > h->level_bs_bytes[l]) h->level_bs_bytes[l] = (int)bs;
+    }
+    // views
+    ProblemView& pv = h->pv;
+    pv.N = N; pv.E = E; pv.M = p.M;
+    pv.ei = h->ei.p; pv.ej = h->ej.p; pv.Z = h->Z.p; pv.drot = h->drot.p; pv.dtrans = h->dtrans.p;
+    pv.dvel = h->dvel.p; pv.dt = h->dt.p;
+    pv.edge_owner = h->edge_owner.p; pv.pair_owner = h->pair_owner.p; pv.part = opts.part;
+    pv.w0 = pv.w1 = pv.w2 = pv.w3 = 1.0;
+    LinBuffers& lb = h->lb;
+    lb.r_vo = h->r_vo.p; lb.J_vo = h->J_vo.p; lb.S_vo = h->S_vo.p; lb.q_vo = h->q_vo.p; lb.r_imu = h->r_imu.p;
+    lb.J_rot = h->J_rot.p; lb.loss_part = h->lin_part.p;
+    AsmView& av = h->av;
+    av.node_eoff = h->d_node_eoff.p; av.node_edges = h->d_node_edges.p; av.pair_lo = h->d_pair_lo.p;
+    av.pair_hi = h->d_pair_hi.p; av.pair_adj = h->d_pair_adj.p; av.pair_eoff = h->d_pair_eoff.p;
+    av.pair_edges = h->d_pair_edges.p; av.P = p.P;
+    FrontMeta& fm = h->fm;
+    fm.np = h->d_np.p; fm.nb = h->d_nb.p; fm.nodes_off = h->d_nodes_off.p; fm.nodes = h->d_nodes.p;
+    fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.child_off = h->d_child_off.p; fm.children = h->d_children.p;
+    fm.cinv_off = h->d_cinv_off.p; fm.cinv = h->d_cinv.p; fm.hmap_off = h->d_hmap_off.p; fm.hmap = h->d_hmap.p;
+    fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p;
+    // LM state
+    LMState s;
+    std::memset(&s, 0, sizeof(s));
+    s.damping = 1.0 / h->prm.radius; s.radius = h->prm.radius; s.down = h->prm.down; s.diag_scale = 1.0;
+    s.need_linearize = 1; s.continual = 1;
+    cudaMemcpy(h->st.p, &s, sizeof(s), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete h; return (int)e; }
+    *out = h;
+    return 0;
+}
+
+extern "C" void islam_pvgo_destroy(islam_pvgo* h) { delete h; }
+
+extern "C" int islam_pvgo_get_dims(const islam_pvgo* h, islam_pvgo_dims* d) {
+    if (!h || !d) return -1;
+    const Plan& p = h->plan;
+    std::memset(d, 0, sizeof(*d));
+    d->N = p.N; d->E = p.E; d->M = p.M; d->P = p.P; d->F = p.F; d->levels = p.n_levels; d->band = p.band;
+    d->root_pivots = p.root_pivots; d->max_rows = p.max_rows; d->max_cols = p.max_cols;
+    d->n_shared_fronts = h->n_shared; d->L_doubles = p.L_doubles; d->U_doubles = p.U_doubles;
+    d->shared_doubles = h->shared_doubles; d->factor_flops = p.factor_flops;
+    return 0;
+}
+
+extern "C" int islam_pvgo_set_problem(islam_pvgo* h, const float* Z, const float* drot, const float* dtrans,
+                                      const float* dvel, const float* dt, const double w[4], void* stream) {
+    if (!h || !drot || !dtrans || !dvel || !dt || !w || (h->plan.E > 0 && !Z)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Plan& p = h->plan;
+    if (p.E) CK(cudaMemcpyAsync(h->Z.p, Z, sizeof(float) * 7 * p.E, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->drot.p, drot, sizeof(float) * 4 * p.M, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->dtrans.p, dtrans, sizeof(float) * 3 * p.M, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->dvel.p, dvel, sizeof(float) * 3 * p.M, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->dt.p, dt, sizeof(float) * p.M, cudaMemcpyDeviceToDevice, s));
+    h->pv.w0 = w[0]; h->pv.w1 = w[1]; h->pv.w2 = w[2]; h->pv.w3 = w[3];
+    if (h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }   // weights are kernel arguments
+    return 0;
+}
+
+extern "C" int islam_pvgo_set_state(islam_pvgo* h, const float* nodes, const float* vels, void* stream) {
+    if (!h || !nodes || !vels) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->nodes[0].p, nodes, sizeof(float) * 7 * h->plan.N, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->vels[0].p, vels, sizeof(float) * 3 * h->plan.N, cudaMemcpyDeviceToDevice, s));
+    k_set_state_flags<<<1, 1, 0, s>>>(h->st.p, 0);
+    return (int)cudaGetLastError();
+}
+
+static int read_state(islam_pvgo* h, cudaStream_t s) {
+    CK(cudaMemcpyAsync(h->st_host, h->st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, void* stream) {
+    if (!h) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = read_state(h, s);
+    if (rc) return rc;
+    int cur = h->st_host->cur;
+    if (nodes) CK(cudaMemcpyAsync(nodes, h->nodes[cur].p, sizeof(float) * 7 * h->plan.N, cudaMemcpyDeviceToDevice, s));
+    if (vels) CK(cudaMemcpyAsync(vels, h->vels[cur].p, sizeof(float) * 3 * h->plan.N, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------------------
+static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
+    const Plan& p = h->plan;
+    double* part = h->lin_part.p;
+    if (h->nblk_vo)
+        k_vo<0><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, force);
+    k_imu<0><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
+                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, force);
+    k_assemble_nodes<<<(p.N * 32 + 127) / 128, 128, 0, s>>>(h->st.p, h->pv, h->lb, h->av, h->Hd.p, h->g.p, force);
+    k_assemble_pairs<<<(p.P * 32 + 127) / 128, 128, 0, s>>>(h->st.p, h->pv, h->lb, h->av, h->Ho.p, force);
+    return (int)cudaGetLastError();
+}
+
+static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int which /*0 local, 2 shared*/) {
+    const Plan& p = h->plan;
+    const islam_lm_params& q = h->prm;
+    for (int l = 0; l < p.n_levels; ++l) {
+        int b = p.level_off[l];
+        int nloc = h->level_nlocal[l];
+        size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
+        if (which == 0 && nloc > 0)
+            k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
+                                                          h->g.p, h->Lbuf.p, h->Ubuf.p, h->shared.p, q.lm_min, q.lm_max,
+                                                          forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail);
+    }
+    return (int)cudaGetLastError();
+}
+
+// number of shared fronts scheduled at level l (they follow the local ones in d_level_fronts)
+static int level_nshared(const islam_pvgo* h, int l) {
+    if (h->opts.n_parts <= 1) return 0;
+    const Plan& p = h->plan;
+    int n = 0;
+    for (int k = p.level_off[l]; k < p.level_off[l + 1]; ++k)
+        if (p.f_part[p.level_fronts[k]] < 0) ++n;
+    return n;
+}
+
+static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_scale) {
+    const Plan& p = h->plan;
+    const islam_lm_params& q = h->prm;
+    for (int l = 0; l < p.n_levels; ++l) {
+        int ns = level_nshared(h, l);
+        if (!ns) continue;
+        int b = p.level_off[l] + h->level_nlocal[l];
+        size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
+        k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
+                                                    h->Lbuf.p, h->Ubuf.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
+                                                    h->level_smem_doubles[l], 2, &h->st.p->chol_fail);
+    }
+    return (int)cudaGetLastError();
+}
+
+static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
+    const Plan& p = h->plan;
+    for (int l = p.n_levels - 1; l >= 0; --l) {
+        int n = h->level_nlocal[l] + level_nshared(h, l);
+        if (!n) continue;
+        k_backsolve_level<<<n, BS_THREADS, (size_t)h->level_bs_bytes[l], s>>>(h->st.p, h->d_level_fronts.p + p.level_off[l],
+                                                                              h->fm, h->Lbuf.p, h->D.p, force);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int islam_pvgo_linearize(islam_pvgo* h, void* stream) {
+    if (!h) return -1;
+    return launch_linearize(h, (cudaStream_t)stream, 1);
+}
+
+extern "C" int islam_pvgo_get_residuals(islam_pvgo* h, float* pgerr, float* adj, float* rot, float* tv, void* stream) {
+    if (!h) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Plan& p = h->plan;
+    if (pgerr && p.E) CK(cudaMemcpyAsync(pgerr, h->r_vo.p, sizeof(float) * 6 * p.E, cudaMemcpyDeviceToDevice, s));
+    if (adj || rot || tv) k_transpose_imu_res<<<(p.M + 127) / 128, 128, 0, s>>>(h->r_imu.p, p.M, adj, rot, tv);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int islam_pvgo_get_normal_eq(islam_pvgo* h, double* Hd, double* Ho, double* g, int32_t* pairs, void* stream) {
+    if (!h) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Plan& p = h->plan;
+    if (Hd) CK(cudaMemcpyAsync(Hd, h->Hd.p, sizeof(double) * 81 * p.N, cudaMemcpyDeviceToDevice, s));
+    if (Ho) CK(cudaMemcpyAsync(Ho, h->Ho.p, sizeof(double) * 81 * p.P, cudaMemcpyDeviceToDevice, s));
+    if (g) CK(cudaMemcpyAsync(g, h->g.p, sizeof(double) * 9 * p.N, cudaMemcpyDeviceToDevice, s));
+    if (pairs) {
+        std::vector<int32_t> pr(2 * (size_t)p.P);
+        for (int i = 0; i < p.P; ++i) { pr[2 * i] = p.pair_lo[i]; pr[2 * i + 1] = p.pair_hi[i]; }
+        CK(cudaMemcpyAsync(pairs, pr.data(), sizeof(int32_t) * pr.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+extern "C" int islam_pvgo_solve(islam_pvgo* h, double diag_scale, double lm_min, double lm_max, double* D, int32_t* info,
+                                void* stream) {
+    if (!h || diag_scale <= 0.0) return -1;
+    if (h->opts.n_parts > 1) return -6;       // testing hook is single-GPU only
+    cudaStream_t s = (cudaStream_t)stream;
+    islam_lm_params saved = h->prm;
+    h->prm.lm_min = lm_min; h->prm.lm_max = lm_max;
+    CK(cudaMemsetAsync(&h->st.p->chol_fail, 0, sizeof(int), s));
+    int rc = launch_factor(h, s, diag_scale, 0);
+    h->prm = saved;
+    if (rc) return rc;
+    rc = launch_backsolve(h, s, 1);
+    if (rc) return rc;
+    if (D) CK(cudaMemcpyAsync(D, h->D.p, sizeof(double) * 9 * h->plan.N, cudaMemcpyDeviceToDevice, s));
+    if (info) {
+        rc = read_state(h, s);
+        if (rc) return rc;
+        *info = h->st_host->chol_fail;
+    }
+    return 0;
+}
+
+// ---- LM driver ------------------------------------------------------------------------------------------------------
+extern "C" int islam_pvgo_lm_reset(islam_pvgo* h, const islam_lm_params* p, void* stream) {
+    if (!h) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p) h->prm = *p;
+    if (h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }
+    int rc = read_state(h, s);
+    if (rc) return rc;
+    LMState st;
+    std::memset(&st, 0, sizeof(st));
+    st.cur = h->st_host->cur;
+    st.damping = 1.0 / h->prm.radius; st.radius = h->prm.radius; st.down = h->prm.down; st.diag_scale = 1.0;
+    st.need_linearize = 1; st.continual = 1;
+    *h->st_host = st;
+    CK(cudaMemcpyAsync(h->st.p, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
+    k_begin_try<<<1, 32, 0, s>>>(h->st.p);
+    int rc = launch_linearize(h, s, 0);
+    if (rc) return rc;
+    k_begin_step<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, h->nblk_vo + h->nblk_imu);
+    rc = launch_factor(h, s, 0.0, 0);
+    if (rc) return rc;
+    if (h->opts.n_parts > 1 && h->n_shared > 0) {
+        k_shared_base<<<h->n_shared, FAC_THREADS, 0, s>>>(h->st.p, h->d_shared_fronts.p, h->fm, h->Hd.p, h->Ho.p, h->g.p,
+                                                          h->Ubuf.p, h->shared.p);
+    }
+    return (int)cudaGetLastError();
+}
+
+static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
+    const Plan& p = h->plan;
+    int rc = 0;
+    if (h->opts.n_parts > 1) { rc = launch_factor_shared(h, s, 0.0); if (rc) return rc; }
+    rc = launch_backsolve(h, s, 0);
+    if (rc) return rc;
+    k_retract<<<(p.N + 127) / 128, 128, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->D.p, p.N);
+    double* part = h->trial_part.p;
+    if (h->nblk_vo)
+        k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
+    k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
+                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
+    k_lm_control<<<1, 256, 0, s>>>(h->st.p, h->prm, part, h->nblk_vo + h->nblk_imu);
+    return (int)cudaGetLastError();
+}
+
+static int enqueue_try(islam_pvgo* h, cudaStream_t s) {
+    int rc = enqueue_try_begin(h, s);
+    if (rc) return rc;
+    return enqueue_try_end(h, s);
+}
+
+extern "C" int islam_pvgo_lm_try(islam_pvgo* h, void* stream) {
+    if (!h) return -1;
+    if (h->opts.n_parts > 1) return -6;
+    return enqueue_try(h, (cudaStream_t)stream);
+}
+
+extern "C" int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream) {
+    if (!h) return -1;
+    return enqueue_try_begin(h, (cudaStream_t)stream);
+}
+extern "C" int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream) {
+    if (!h) return -1;
+    return enqueue_try_end(h, (cudaStream_t)stream);
+}
+extern "C" int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n) {
+    if (!h || !dev_ptr || !n) return -1;
+    *dev_ptr = h->shared.p;
+    *n = h->shared_doubles;
+    return 0;
+}
+
+// one try through a CUDA graph captured on first use (kernel arguments are fixed; all control state is on the device)
+static int graph_try(islam_pvgo* h, cudaStream_t s) {
+    if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return enqueue_try(h, s);   // not capturable
+    if (!h->graph_try || h->graph_stream != s) {
+        if (h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_try(h, s);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(e);
+        e = cudaGraphInstantiate(&h->graph_try, g, 0);
+        cudaGraphDestroy(g);
+        CK(e);
+        h->graph_stream = s;
+    }
+    CK(cudaGraphLaunch(h->graph_try, s));
+    return 0;
+}
+
+extern "C" int islam_pvgo_lm_step(islam_pvgo* h, islam_lm_state* out, void* stream) {
+    if (!h) return -1;
+    if (h->opts.n_parts > 1) return -6;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = read_state(h, s);
+    if (rc) return rc;
+    int target = h->st_host->steps_done + 1;
+    // optimizer.step ignores the scheduler: force one step even if `continual` was cleared
+    if (!h->st_host->continual) {
+        int one = 1;
+        CK(cudaMemcpyAsync(&h->st.p->continual, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    for (int guard = 0; guard < 64; ++guard) {
+        rc = graph_try(h, s);
+        if (rc) return rc;
+        rc = read_state(h, s);
+        if (rc) return rc;
+        if (h->st_host->steps_done >= target) break;
+    }
+    if (out) *out = *h->st_host;
+    return 0;
+}
+
+extern "C" int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out, void* stream) {
+    if (!h) return -1;
+    if (h->opts.n_parts > 1) return -6;
+    cudaStream_t s = (cudaStream_t)stream;
+    int budget = h->prm.max_steps + 2;          // speculative: a couple of rejected tries cost no extra sync
+    for (int guard = 0; guard < 64; ++guard) {
+        for (int k = 0; k < budget; ++k) {
+            int rc = graph_try(h, s);
+            if (rc) return rc;
+        }
+        int rc = read_state(h, s);
+        if (rc) return rc;
+        if (!h->st_host->continual) break;
+        budget = 4;
+    }
+    if (out) *out = *h->st_host;
+    return 0;
+}
+
+extern "C" int islam_pvgo_get_lm_state(islam_pvgo* h, islam_lm_state* out, void* stream) {
+    if (!h || !out) return -1;
+    int rc = read_state(h, (cudaStream_t)stream);
+    if (rc) return rc;
+    *out = *h->st_host;
+    return 0;
+}
+
+// ---- outer losses / alignment ---------------------------------------------------------------------------------------
+extern "C" int islam_pvgo_vo_loss(islam_pvgo* h, const float* P, float* tl, float* rl, float* gt, float* gr, void* stream) {
+    if (!h || !P || !tl || !rl || ((gt == nullptr) != (gr == nullptr))) return -1;
+    const Plan& p = h->plan;
+    if (!p.E) return 0;
+    k_vo_loss<<<(p.E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->ei.p, h->ej.p,
+                                                                  P, p.E, tl, rl, gt, gr);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int islam_pvgo_imu_loss(islam_pvgo* h, float* tl, float* rl, void* stream) {
+    if (!h || !tl || !rl) return -1;
+    const Plan& p = h->plan;
+    k_imu_loss<<<(p.M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
+                                                                   h->vels[1].p, h->drot.p, h->dvel.p, p.M, tl, rl);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int islam_pvgo_align(islam_pvgo* h, const float* target, float* nout, float* vout, void* stream) {
+    if (!h || !target || !nout || !vout) return -1;
+    const Plan& p = h->plan;
+    k_align<<<(p.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
+                                                                h->vels[1].p, target, p.N, nout, vout);
+    return (int)cudaGetLastError();
+}
+
+// ---- host-only introspection of the symbolic plan (no GPU needed; used by the CPU test-suite) -------------------------
+struct islam_plan { Plan plan; };
+
+extern "C" int islam_plan_build(islam_plan** out, int32_t N, int32_t E, const int64_t* links, const islam_pvgo_opts* o) {
+    if (!out) return -1;
+    SymbolicOpts so;
+    if (o) {
+        if (o->band_max > 0) so.band_max = o->band_max;
+        if (o->leaf_max > 0) so.leaf_max = o->leaf_max;
+        if (o->pivot_max > 0) so.pivot_max = o->pivot_max;
+        if (o->n_parts > 0) so.n_parts = o->n_parts;
+    }
+    islam_plan* pl = new (std::nothrow) islam_plan();
+    if (!pl) return -1;
+    int rc = build_plan(N, E, links, so, pl->plan);
+    if (rc) { delete pl; return rc; }
+    *out = pl;
+    return 0;
+}
+extern "C" void islam_plan_free(islam_plan* pl) { delete pl; }
+extern "C" int64_t islam_plan_array(const islam_plan* pl, const char* name, const void** ptr) {
+    if (!pl || !name || !ptr) return -1;
+    const Plan& p = pl->plan;
+#define ARR(nm, vec) if (!std::strcmp(name, nm)) { *ptr = (vec).data(); return (int64_t)(vec).size(); }
+    ARR("pair_lo", p.pair_lo) ARR("pair_hi", p.pair_hi) ARR("pair_adj", p.pair_adj) ARR("pair_eoff", p.pair_eoff)
+    ARR("pair_edges", p.pair_edges) ARR("node_eoff", p.node_eoff) ARR("node_edges", p.node_edges)
+    ARR("edge_pair", p.edge_pair) ARR("f_np", p.f_np) ARR("f_nb", p.f_nb) ARR("f_nodes_off", p.f_nodes_off)
+    ARR("f_nodes", p.f_nodes) ARR("f_Loff", p.f_Loff) ARR("f_Uoff", p.f_Uoff) ARR("f_parent", p.f_parent)
+    ARR("f_level", p.f_level) ARR("f_part", p.f_part) ARR("f_child_off", p.f_child_off) ARR("f_children", p.f_children)
+    ARR("c_inv_off", p.c_inv_off) ARR("c_inv", p.c_inv) ARR("f_hmap_off", p.f_hmap_off) ARR("hmap", p.hmap)
+    ARR("level_off", p.level_off) ARR("level_fronts", p.level_fronts) ARR("node_front", p.node_front)
+    ARR("node_slot", p.node_slot) ARR("node_pos", p.node_pos)
+#undef ARR
+    return -1;
+}
