@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its config[1]:
+LM iterations/s (and factors/s) of the 5 000-pose / 49 962-factor synthetic PVGO (C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over the graph: `run_pvgo`'s optimisation loop (/root/reference/pvgo.py:177-180)
+run for exactly 10 `optimizer.step` calls from the dead-reckoned initial guess (scheduler bypassed so every step does
+the same work).  `value` = LM iterations / second with inputs already resident in HBM; `e2e` = the same metric
+through the reference-facing call `islam_b200.pvgo.run_pvgo(...)` fed HOST tensors (H2D of every input, D2H of
+nodes / velocities / losses inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LM_ITERS = 10                 # optimizer.step calls per step (StopOnPlateau's max steps, pvgo.py:172)
+SURVEY_BYTES_PER_ITER = 62e6  # SURVEY.md 8d compact fp32 byte model of one LM iteration @C2
+SURVEY_BYTES_FACTOR = 21.6e6  # read H (7.7 MB) + write L (13.9 MB): the factorisation's share of the above
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.p, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+        return self
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.p:
+            time.sleep(0.15)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def _graph():
+    from islam_b200 import synth
+    return synth.config2()
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def time_oracle(g, iters, dtype=np.float64):
+    """The CPU restatement (oracle.SparseLM: same normal equations, banded LAPACK Cholesky) for `iters` LM steps."""
+    from oracle import pvgo_oracle as po
+    lm = po.SparseLM(g, dtype)
+    t0 = time.perf_counter()
+    lm.run(steps=iters)
+    return time.perf_counter() - t0, lm
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    g = _graph()
+    sample_iters = 2
+    for _ in range(min(args.warmup, 1)):
+        time_oracle(g, 1)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _lm = time_oracle(g, sample_iters)
+        t += dt
+    its = sample_iters * args.steps / t
+    cores = os.cpu_count()
+    out = {
+        'impl': 'reference', 'metric': 'LM iterations/s on the 5k-pose PVGO (C2)', 'value': its, 'unit': 'LM it/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'factors_per_s': its * g.factors,
+        'config': {'workload': 'C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows',
+                   'parallelism': 'host CPU'},
+        'cpu_baseline': {'value': its, 'unit': 'LM it/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample_iters} LM iterations of C2 per step (oracle.SparseLM float64: NumPy assembly + '
+                                   f'LAPACK banded Cholesky; PyPose itself is absent and its dense algorithm needs 324 GB at C2)'},
+        'e2e': {'value': its, 'unit': 'LM it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device — the B200 kernels are the only implementation (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from islam_b200.solver import PVGOSolver
+    from islam_b200 import pvgo as ipvgo
+
+    g = _graph()
+    F = g.factors
+    s = PVGOSolver(g.N, g.links, device=dev)
+    s.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
+    nodes0 = torch.as_tensor(g.init_nodes, device=dev)
+    vels0 = torch.as_tensor(g.init_vels, device=dev)
+
+    def one_step():
+        s.set_state(nodes0, vels0)                    # D2D: inputs are resident in HBM
+        s.lm_reset(radius=g.radius, max_steps=LM_ITERS, use_scheduler=0)
+        return s.lm_run()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        st = one_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tries = 0
+    with ClockSampler(local_rank) as clk:
+        with torch.cuda.stream(s.stream):
+            e0.record()
+            for _ in range(args.steps):
+                st = one_step()
+                tries += st.tries_total
+            e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    iters_total = LM_ITERS * args.steps * world          # weak scaling: every rank solves its own C2 replica
+    value = iters_total / (ms * 1e-3)
+    launches = tries * (10 + 2 * s.dims.levels)
+
+    # ---- per-phase device time of one try (CUDA events on the solver's stream) -> roofline of the dominant kernel
+    one_step()
+    s.set_state(nodes0, vels0)
+    s.lm_reset(radius=g.radius, max_steps=LM_ITERS, use_scheduler=0)
+    ph = [s.profile_try() for _ in range(LM_ITERS)]
+    fac_ms = float(np.mean([p['factor'] for p in ph]))
+    per_launch_s = fac_ms * 1e-3 / s.dims.levels
+    peak, peak_src = _peaks()
+    achieved = SURVEY_BYTES_FACTOR / (fac_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': f'k_factor_level x{s.dims.levels} (multifrontal fp64 Cholesky of one LM try)',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'algorithmic_bytes_per_factorisation': SURVEY_BYTES_FACTOR,
+                'avg_launch_us': per_launch_s * 1e6,
+                'phases_ms': {k: float(np.mean([p[k] for p in ph])) for k in ph[0]},
+                'whole_iteration': {'achieved': SURVEY_BYTES_PER_ITER / (ms * 1e-3 / (LM_ITERS * args.steps)) / 1e9,
+                                    'frac': SURVEY_BYTES_PER_ITER / (ms * 1e-3 / (LM_ITERS * args.steps)) / 1e9 / peak}}
+    tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tr):
+        try:
+            roofline['traffic'] = json.load(open(tr)).get('k_factor_level_bytes_per_launch')
+        except Exception:
+            pass
+
+    # ---- e2e: the reference-facing call with HOST tensors (pinned), H2D + D2H inside the timed region
+    host = {k: torch.as_tensor(getattr(g, k)).pin_memory() for k in
+            ('init_nodes', 'init_vels', 'vo_motions', 'dts', 'imu_drots', 'imu_dtrans', 'imu_dvels')}
+    links = torch.as_tensor(g.links)
+
+    def e2e_step():
+        tl, rl, n, v, _ = ipvgo.run_pvgo(host['init_nodes'], host['init_vels'], host['vo_motions'], links, host['dts'],
+                                         host['imu_drots'], host['imu_dtrans'], host['imu_dvels'], device=dev,
+                                         radius=g.radius, loss_weight=g.loss_weight, use_scheduler=False,
+                                         max_steps=LM_ITERS)
+        return float(tl.sum().item() + rl.sum().item()), n, v
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = LM_ITERS * n_e2e * world / float(te.item())
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = (g.N * 7 + g.N * 3 + 2 * g.E) * 4
+    e2e = {'value': e2e_val, 'unit': 'LM it/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'api': 'islam_b200.pvgo.run_pvgo (mirror of reference pvgo.py:122-205), host tensors in, host tensors out'}
+
+    out = {
+        'metric': 'LM iterations/s on the 5k-pose PVGO (C2)', 'value': value, 'unit': 'LM it/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 residuals/Jacobians, f64 normal equations + Cholesky',
+        'data': 'synthetic', 'factors_per_s': value * F, 'residual_rows_per_s': value * g.rows,
+        'config': {'workload': 'C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows; '
+                               f'{LM_ITERS} fixed LM iterations per step, loss_weight (1,0.1,10,0.1), radius 1e4',
+                   'parallelism': 'single GPU' if world == 1 else f'replicas x{world} (one C2 graph per GPU, no collective)',
+                   'l2': f'working set (L {s.dims.L_doubles * 8 / 1e6:.0f} MB + U {s.dims.U_doubles * 8 / 1e6:.0f} MB '
+                         'fp64 panels) exceeds the 126 MB L2; no explicit flush'},
+        'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+        'lm': {'final_loss': st.loss, 'steps_done': st.steps_done, 'tries': st.tries_total, 'info': st.info},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_cpu, _ = time_oracle(g, 10)
+        out['cpu_baseline'] = {'value': 10 / t_cpu, 'unit': 'LM it/s', 'cores': os.cpu_count(), 'kind': 'port',
+                               'sample': '10 LM iterations of C2 (oracle.SparseLM float64: NumPy assembly + LAPACK banded '
+                                         'Cholesky, same normal equations; literal dense PyPose needs 324 GB at C2)'}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -121,6 +121,9 @@ int islam_pvgo_lm_step(islam_pvgo* h, islam_lm_state* out /* may be NULL */, voi
  * synchronises once at the end (again only if rejected tries exhausted the speculative budget) */
 int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out /* may be NULL */, void* stream);
 int islam_pvgo_get_lm_state(islam_pvgo* h, islam_lm_state* out, void* stream); /* synchronises */
+/* one try timed phase by phase with CUDA events on `stream` (ms[5]: linearise, factor, back-substitution,
+ * retract + trial loss + control, total); synchronises — measurement aid for bench.py's roofline object */
+int islam_pvgo_profile_try(islam_pvgo* h, float* ms, void* stream);
 /* multi-GPU: a try split around the single all-reduce of the shared (separator) panels */
 int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream);
 int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);

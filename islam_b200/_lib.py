@@ -64,6 +64,7 @@ _SIGS = {
     'islam_pvgo_lm_step': (C.c_int, [_P, C.POINTER(LMState), _P]),
     'islam_pvgo_lm_run': (C.c_int, [_P, C.POINTER(LMState), _P]),
     'islam_pvgo_get_lm_state': (C.c_int, [_P, C.POINTER(LMState), _P]),
+    'islam_pvgo_profile_try': (C.c_int, [_P, C.POINTER(C.c_float * 5), _P]),
     'islam_pvgo_lm_try_begin': (C.c_int, [_P, _P]),
     'islam_pvgo_shared_buffer': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     'islam_pvgo_lm_try_end': (C.c_int, [_P, _P]),

@@ -166,7 +166,7 @@ struct islam_pvgo {
     DevBuf<int> d_np, d_nb, d_nodes_off, d_nodes, d_child_off, d_children, d_cinv_off, d_cinv, d_hmap_off, d_hmap,
         d_part, d_level_fronts, d_shared_fronts;
     DevBuf<long long> d_Loff, d_Uoff, d_shared_off;
-    DevBuf<double> Lbuf, Ubuf, shared;
+    DevBuf<double> Lbuf, Ubuf, Linv, shared;
     DevBuf<LMState> st;
     LMState* st_host = nullptr;     // pinned mirror
     int nblk_vo = 0, nblk_imu = 0;
@@ -191,7 +191,7 @@ struct islam_pvgo {
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot};
         for (auto* b : fb) b->release();
-        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &shared};
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared};
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_shared_off.release();
         st.release();
@@ -301,7 +301,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         AL(shared, (size_t)h->shared_doubles);
         cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
     }
-    AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles);
+    AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles); AL(Linv, 81 * (size_t)N);
     AL(st, 1);
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
@@ -319,9 +319,12 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     for (int f = 0; f < p.F; ++f) {
         int l = p.f_level[f];
         long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
-        long long need = Rf * Cf + 96;
-        if (need <= h->max_smem_doubles && need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;
-        long long bs = (Rb + Cf + Cf * (Cf + 1)) * 8;
+        int nch = p.f_child_off[f + 1] - p.f_child_off[f];
+        long long meta = front_meta_doubles(p.f_np[f], p.f_np[f] + p.f_nb[f], nch);
+        long long need = Rf * Cf + 96 + meta;
+        if (need > h->max_smem_doubles) need = 96 + meta;        // panel stays in global memory
+        if (need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;
+        long long bs = (Rb + Cf + 16) * 8;
         if (bs > max_optin - 1024) { delete h; return -5; }       // boundary too wide for the back-substitution kernel
         if (bs > h->level_bs_bytes[l]) h->level_bs_bytes[l] = (int)bs;
     }
@@ -432,7 +435,7 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
         if (which == 0 && nloc > 0)
             k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
-                                                          h->g.p, h->Lbuf.p, h->Ubuf.p, h->shared.p, q.lm_min, q.lm_max,
+                                                          h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
                                                           forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail);
     }
     return (int)cudaGetLastError();
@@ -457,7 +460,7 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
         int b = p.level_off[l] + h->level_nlocal[l];
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
         k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
-                                                    h->Lbuf.p, h->Ubuf.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
+                                                    h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
                                                     h->level_smem_doubles[l], 2, &h->st.p->chol_fail);
     }
     return (int)cudaGetLastError();
@@ -469,7 +472,7 @@ static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
         int n = h->level_nlocal[l] + level_nshared(h, l);
         if (!n) continue;
         k_backsolve_level<<<n, BS_THREADS, (size_t)h->level_bs_bytes[l], s>>>(h->st.p, h->d_level_fronts.p + p.level_off[l],
-                                                                              h->fm, h->Lbuf.p, h->D.p, force);
+                                                                              h->fm, h->Lbuf.p, h->Linv.p, h->D.p, force);
     }
     return (int)cudaGetLastError();
 }
@@ -572,6 +575,41 @@ static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
     k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
                                                   h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
     k_lm_control<<<1, 256, 0, s>>>(h->st.p, h->prm, part, h->nblk_vo + h->nblk_imu);
+    return (int)cudaGetLastError();
+}
+
+// one try with CUDA events between its phases (bench.py's live roofline measurement); synchronises
+extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise, factor, backsolve, trial+control, total */,
+                                      void* stream) {
+    if (!h || !ms) return -1;
+    if (h->opts.n_parts > 1) return -6;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Plan& p = h->plan;
+    cudaEvent_t ev[5];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    int rc = 0;
+    CK(cudaEventRecord(ev[0], s));
+    k_begin_try<<<1, 32, 0, s>>>(h->st.p);
+    rc = launch_linearize(h, s, 0);
+    k_begin_step<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, h->nblk_vo + h->nblk_imu);
+    CK(cudaEventRecord(ev[1], s));
+    if (!rc) rc = launch_factor(h, s, 0.0, 0);
+    CK(cudaEventRecord(ev[2], s));
+    if (!rc) rc = launch_backsolve(h, s, 0);
+    CK(cudaEventRecord(ev[3], s));
+    k_retract<<<(p.N + 127) / 128, 128, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->D.p, p.N);
+    double* part = h->trial_part.p;
+    if (h->nblk_vo)
+        k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
+    k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
+                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
+    k_lm_control<<<1, 256, 0, s>>>(h->st.p, h->prm, part, h->nblk_vo + h->nblk_imu);
+    CK(cudaEventRecord(ev[4], s));
+    CK(cudaStreamSynchronize(s));
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+    cudaEventElapsedTime(&ms[4], ev[0], ev[4]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
     return (int)cudaGetLastError();
 }
 

@@ -85,29 +85,148 @@ __device__ __forceinline__ bool chol9(const double* __restrict__ Dblk, double* L
     return ok;
 }
 
+// ---- per-front metadata staged in shared memory -------------------------------------------------------------
+// The gathers below touch the maps once per matrix element; chasing them through L2 (5-6 dependent loads per
+// element) made a single front cost ~240 us, so a CTA copies everything it needs into shared memory first.
+constexpr int MAXC = 6;      // children handled on the fast path (more => generic global-memory path)
+constexpr int MAXS = 40;     // slots (pivot + boundary poses) handled on the fast path
+
+struct FrontCtx {
+    int np, nb, ns, nch;
+    bool fast;
+    const int* nodes;        // [ns]            (shared or global)
+    const int* hmap;         // [ns*np]
+    const int* inv;          // [nch][ns]       parent slot -> child boundary idx | -1   (fast path only)
+    const int* cnb;          // [nch]
+    const int* cshared;      // [nch] 1 if the child is a shared (multi-GPU) front
+    const long long* cU;     // [nch] offset of the child's U
+};
+
+__host__ __device__ __forceinline__ int front_meta_doubles(int np, int ns, int nch) {
+    if (nch > MAXC || ns > MAXS) return 0;
+    int ints = 2 * MAXC /* long long offsets */ + ns + ns * np + nch * ns + 2 * nch;
+    return (ints + 1) / 2 + 1;
+}
+
+__device__ __forceinline__ void stage_front(const FrontMeta& m, int f, int* si, FrontCtx& c) {
+    c.np = m.np[f]; c.nb = m.nb[f]; c.ns = c.np + c.nb;
+    const int k0 = m.child_off[f];
+    c.nch = m.child_off[f + 1] - k0;
+    c.fast = (c.nch <= MAXC && c.ns <= MAXS);
+    const int* gn = m.nodes + m.nodes_off[f];
+    const int* gh = m.hmap + m.hmap_off[f];
+    if (!c.fast) { c.nodes = gn; c.hmap = gh; c.inv = nullptr; c.cnb = nullptr; c.cshared = nullptr; c.cU = nullptr; return; }
+    long long* sU = (long long*)si;                 // 8-byte aligned: first in the region
+    int* sn = si + 2 * MAXC;
+    int* sh = sn + c.ns;
+    int* sv = sh + c.ns * c.np;
+    int* sb = sv + c.nch * c.ns;
+    int* ss = sb + c.nch;
+    for (int i = threadIdx.x; i < c.ns; i += blockDim.x) sn[i] = gn[i];
+    for (int i = threadIdx.x; i < c.ns * c.np; i += blockDim.x) sh[i] = gh[i];
+    for (int i = threadIdx.x; i < c.nch * c.ns; i += blockDim.x) {
+        int k = i / c.ns, s_ = i - k * c.ns;
+        sv[i] = m.cinv[m.cinv_off[k0 + k] + s_];
+    }
+    for (int k = threadIdx.x; k < c.nch; k += blockDim.x) {
+        int ch = m.children[k0 + k];
+        sb[k] = m.nb[ch];
+        ss[k] = m.part[ch] < 0;
+        sU[k] = m.Uoff[ch];
+    }
+    c.nodes = sn; c.hmap = sh; c.inv = sv; c.cnb = sb; c.cshared = ss; c.cU = sU;
+}
+
+// gather of the children's update matrices at (row slot rs | -1 = rhs, dof a ; col slot cs, dof b)
+// mode 0: all children, 1: shared children only, 2: private children only
+__device__ __forceinline__ double pull(const FrontCtx& c, const FrontMeta& m, const double* __restrict__ Ubuf, int f,
+                                       int rs, int a, int cs, int b, int mode) {
+    if (!c.fast) return pull_children(m, Ubuf, f, c.ns, rs, a, cs, b, mode);
+    double v = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < c.nch; ++k) {
+        if (mode == 1 && !c.cshared[k]) continue;
+        if (mode == 2 && c.cshared[k]) continue;
+        const int* inv = c.inv + k * c.ns;
+        int cc = inv[cs];
+        if (cc < 0) continue;
+        int nbc = c.cnb[k];
+        int rc;
+        if (rs < 0) rc = 9 * nbc;
+        else {
+            int t = inv[rs];
+            if (t < 0) continue;
+            rc = 9 * t + a;
+        }
+        v += Ubuf[c.cU[k] + rc + (long long)(9 * cc + b) * (9 * nbc + 1)];
+    }
+    return v;
+}
+
+__device__ __forceinline__ double orig(const FrontCtx& c, int rs, int a, int cs, int b, const double* __restrict__ Hd,
+                                       const double* __restrict__ Ho, const double* __restrict__ g, double scale,
+                                       double lm_min, double lm_max, bool damp) {
+    int nc = c.nodes[cs];
+    if (rs < 0) return -g[9 * (size_t)nc + b];                      // b = -J^T W r
+    if (rs == cs) {
+        double v = Hd[81 * (size_t)nc + 9 * a + b];
+        if (a == b && damp) v = fmin(fmax(v, lm_min), lm_max) * scale;
+        return v;
+    }
+    int h = c.hmap[rs * c.np + cs];
+    if (h < 0) return 0.0;
+    const double* blk = Ho + 81 * (size_t)(h >> 1);
+    return (h & 1) ? blk[9 * b + a] : blk[9 * a + b];
+}
+
+// column `col` of the inverse of the 9x9 lower-triangular Lk (forward substitution of e_col), unrolled
+__device__ __forceinline__ void tri_inv_col(const double* Lk, const double* linv, int col, double* __restrict__ out /*[9][9] row-major*/) {
+#pragma unroll
+    for (int c0 = 0; c0 < 9; ++c0) {
+        if (c0 == col) {
+            double x[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                if (i < c0) { x[i] = 0.0; continue; }
+                if (i == c0) { x[i] = linv[i]; continue; }
+                double s = 0.0;
+#pragma unroll
+                for (int k = c0; k < i; ++k) s += Lk[i * (i + 1) / 2 + k] * x[k];
+                x[i] = -s * linv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) out[9 * i + c0] = x[i];
+        }
+    }
+}
+
 // ---- numeric factorisation of one level ------------------------------------------------------------------
-// stage: 0 = all fronts of this launch are local (assemble from H and all children)
-//        1 = "base" pass of shared fronts (multi-GPU): write orig + private-children sums into `shared`
-//        2 = shared fronts after the all-reduce: assemble from `shared` + shared children
+// stage: 0 = local fronts (assemble from H and all children)
+//        2 = shared fronts after the all-reduce (multi-GPU): assemble from `shared` + shared children
+// Linv: per pivot pose the inverse of its 9x9 diagonal Cholesky block (row-major), for the back-substitution.
 __global__ void __launch_bounds__(FAC_THREADS, 1)
 k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
                const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
-               double* __restrict__ Lbuf, double* __restrict__ Ubuf, const double* __restrict__ shared,
-               double lm_min, double lm_max, double forced_scale, int smem_doubles, int stage, int* chol_fail) {
+               double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
+               const double* __restrict__ shared, double lm_min, double lm_max, double forced_scale, int smem_doubles,
+               int stage, int* chol_fail) {
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x;
     extern __shared__ double smem[];
-    const int np = m.np[f], nb = m.nb[f], ns = np + nb;
+    double* Dblk = smem;                       // 81 doubles (+ pad)
+    FrontCtx c;
+    stage_front(m, f, (int*)(smem + 96), c);
+    const int np = c.np, nb = c.nb;
     const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ld = Rf, ub = Rb + 1;
-    const int* nodes = m.nodes + m.nodes_off[f];
+    const int meta_doubles = front_meta_doubles(np, c.ns, c.nch);
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
-    const bool in_smem = (Rf * Cf + 96 <= smem_doubles);
-    double* Dblk = smem;                       // 81 doubles
-    double* P = in_smem ? smem + 96 : Lg;
-    const double* base = (stage == 2) ? shared + m.shared_off[f] : nullptr;   // Rf x Rf column-major
+    const bool in_smem = (96 + meta_doubles + Rf * Cf <= smem_doubles);
+    double* P = in_smem ? smem + 96 + meta_doubles : Lg;
+    const double* base = (stage == 2) ? shared + m.shared_off[f] : nullptr;   // Rf x Rf column-major (+ Cf diag)
+    __syncthreads();
 
     // A. assemble the panel
     for (int idx = tid; idx < Rf * Cf; idx += FAC_THREADS) {
@@ -121,10 +240,10 @@ k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, F
                 v = base[i + (long long)j * Rf];
                 if (i == j)                     // all-reduced original diagonal: clamp, then cumulative damping (A.4)
                     v += fmin(fmax(base[(long long)Rf * Rf + j], lm_min), lm_max) * scale;
-                v += pull_children(m, Ubuf, f, ns, rs, a, cs, b, 1);
+                v += pull(c, m, Ubuf, f, rs, a, cs, b, 1);
             } else {
-                v = orig_entry(m, f, np, nodes, rs, a, cs, b, Hd, Ho, g, scale, lm_min, lm_max, true);
-                v += pull_children(m, Ubuf, f, ns, rs, a, cs, b, 0);
+                v = orig(c, rs, a, cs, b, Hd, Ho, g, scale, lm_min, lm_max, true);
+                v += pull(c, m, Ubuf, f, rs, a, cs, b, 0);
             }
         }
         P[i + (long long)j * ld] = v;
@@ -139,19 +258,19 @@ k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, F
         for (int i = c0 + tid; i < Rf; i += FAC_THREADS) {
             double acc[9];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) acc[c] = P[i + (long long)(c0 + c) * ld];
+            for (int q = 0; q < 9; ++q) acc[q] = P[i + (long long)(c0 + q) * ld];
             for (int k = 0; k < c0; ++k) {
                 double a = P[i + (long long)k * ld];
                 const double* col = P + (long long)k * ld + c0;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) acc[c] -= a * col[c];
+                for (int q = 0; q < 9; ++q) acc[q] -= a * col[q];
             }
             if (i < c0 + 9) {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) Dblk[9 * (i - c0) + c] = acc[c];
+                for (int q = 0; q < 9; ++q) Dblk[9 * (i - c0) + q] = acc[q];
             } else {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) P[i + (long long)(c0 + c) * ld] = acc[c];
+                for (int q = 0; q < 9; ++q) P[i + (long long)(c0 + q) * ld] = acc[q];
             }
         }
         __syncthreads();
@@ -162,21 +281,22 @@ k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, F
             if (i < c0 + 9) {
                 int rr = i - c0;
 #pragma unroll
-                for (int c = 0; c < 9; ++c)
+                for (int q = 0; q < 9; ++q)
 #pragma unroll
                     for (int r2 = 0; r2 < 9; ++r2)
-                        if (r2 == rr) P[i + (long long)(c0 + c) * ld] = (c <= r2) ? Lk[r2 * (r2 + 1) / 2 + (c <= r2 ? c : 0)] : 0.0;
+                        if (r2 == rr) P[i + (long long)(c0 + q) * ld] = (q <= r2) ? Lk[r2 * (r2 + 1) / 2 + (q <= r2 ? q : 0)] : 0.0;
+                tri_inv_col(Lk, linv, rr, Linv + 81 * (size_t)c.nodes[jb]);
             } else {
                 double x[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    double s = P[i + (long long)(c0 + c) * ld];
+                for (int q = 0; q < 9; ++q) {
+                    double s_ = P[i + (long long)(c0 + q) * ld];
 #pragma unroll
-                    for (int k = 0; k < c; ++k) s -= x[k] * Lk[c * (c + 1) / 2 + k];
-                    x[c] = s * linv[c];
+                    for (int k = 0; k < q; ++k) s_ -= x[k] * Lk[q * (q + 1) / 2 + k];
+                    x[q] = s_ * linv[q];
                 }
 #pragma unroll
-                for (int c = 0; c < 9; ++c) P[i + (long long)(c0 + c) * ld] = x[c];
+                for (int q = 0; q < 9; ++q) P[i + (long long)(c0 + q) * ld] = x[q];
             }
         }
         __syncthreads();
@@ -220,17 +340,17 @@ k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, F
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
-                    int r = r0 + x, s = s0 + y;
-                    if (r < ub && s < ub && r >= s && !(r == ub - 1 && s == ub - 1)) {
-                        int cs = np + s / 9, b = s % 9;
+                    int r = r0 + x, s_ = s0 + y;
+                    if (r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1)) {
+                        int cs = np + s_ / 9, b = s_ % 9;
                         int rs = (r == ub - 1) ? -1 : np + r / 9;
                         int a = (rs < 0) ? 0 : r % 9;
                         double v;
                         if (stage == 2)
-                            v = base[(Cf + r) + (long long)(Cf + s) * Rf] + pull_children(m, Ubuf, f, ns, rs, a, cs, b, 1);
+                            v = base[(Cf + r) + (long long)(Cf + s_) * Rf] + pull(c, m, Ubuf, f, rs, a, cs, b, 1);
                         else
-                            v = pull_children(m, Ubuf, f, ns, rs, a, cs, b, 0);
-                        Ug[r + (long long)s * ub] = v - acc[x][y];
+                            v = pull(c, m, Ubuf, f, rs, a, cs, b, 0);
+                        Ug[r + (long long)s_ * ub] = v - acc[x][y];
                     }
                 }
         }
@@ -270,30 +390,28 @@ k_shared_base(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
 }
 
 // ---- back-substitution of one level (root first) --------------------------------------------------------
+// x_p = L11^-T (y_p - L21^T x_b), blocked by pose: the inverse 9x9 diagonal blocks were stored by the factor
+// kernel, so every block step is a 9x9 mat-vec followed by a 9-deep update of the earlier unknowns.
 __global__ void __launch_bounds__(BS_THREADS)
 k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
-                  const double* __restrict__ Lbuf, double* __restrict__ D, int force) {
+                  const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force) {
     if (!force && !st->active) return;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     extern __shared__ double smem[];
     const int np = m.np[f], nb = m.nb[f];
-    const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ld = Rf, ldt = Cf + 1;
+    const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ld = Rf;
     const int* nodes = m.nodes + m.nodes_off[f];
     const double* Lg = Lbuf + m.Loff[f];
     double* xb = smem;                 // [Rb]
     double* ts = xb + Rb;              // [Cf]
-    double* LT = ts + Cf;              // [Cf x ldt] L11 transposed: LT[k + c*ldt] = L[c,k]
+    double* xs = ts + Cf;              // [9] current block solution
     for (int r = tid; r < Rb; r += BS_THREADS) {
         int slot = np + r / 9;
         xb[r] = D[9 * (size_t)nodes[slot] + (r % 9)];
     }
-    for (int idx = tid; idx < Cf * Cf; idx += BS_THREADS) {
-        int k = idx / Cf, c = idx - k * Cf;      // element L[c,k], c fastest (coalesced global read)
-        LT[k + c * ldt] = (c >= k) ? Lg[c + (long long)k * ld] : 0.0;
-    }
     __syncthreads();
-    // ts[c] = y[c] - sum_r L21[r,c] xb[r]
+    // ts[c] = y[c] - sum_r L21[r,c] xb[r]      (one warp per column, coalesced)
     for (int c = w; c < Cf; c += BS_THREADS / 32) {
         const double* col = Lg + (long long)c * ld + Cf;
         double s = 0.0;
@@ -302,17 +420,26 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
         if (lane == 0) ts[c] = col[Rb] - s;       // rhs row holds y = L11^-1 (b - ...)
     }
     __syncthreads();
-    // L11^T x = ts, column-oriented, one warp
-    if (w == 0) {
-        for (int c = Cf - 1; c >= 0; --c) {
-            double xc = ts[c] / LT[c + c * ldt];
-            __syncwarp();
-            if (lane == 0) ts[c] = xc;
-            for (int k = lane; k < c; k += 32) ts[k] -= LT[k + c * ldt] * xc;
-            __syncwarp();
+    for (int jb = np - 1; jb >= 0; --jb) {
+        const int c0 = 9 * jb;
+        if (tid < 9) {                             // x_blk = Lkk^-T ts_blk :  x[a] = sum_{b>=a} Linv[b][a] ts[b]
+            const double* Li = Linv + 81 * (size_t)nodes[jb];
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) s += (b >= tid) ? Li[9 * b + tid] * ts[c0 + b] : 0.0;
+            xs[tid] = s;
         }
+        __syncthreads();
+        if (tid < 9) ts[c0 + tid] = xs[tid];
+        for (int k = tid; k < c0; k += BS_THREADS) {   // ts[k] -= sum_{c in blk} L[c,k] x[c]   (column k, rows c0..c0+8)
+            const double* col = Lg + (long long)k * ld + c0;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) s += col[q] * xs[q];
+            ts[k] -= s;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int c = tid; c < Cf; c += BS_THREADS) D[9 * (size_t)nodes[c / 9] + (c % 9)] = ts[c];
 }
 

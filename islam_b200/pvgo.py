@@ -1,0 +1,179 @@
+"""Drop-in mirror of /root/reference/pvgo.py on top of the B200 kernels.
+
+Same names, argument meaning, return order and error behaviour as the reference module:
+
+    PoseVelGraph(nodes, vels)                      pvgo.py:15-23
+        .forward(edges, poses, imu_drots, imu_dtrans, imu_dvels, dts)      pvgo.py:26-64
+        .vo_loss(edges, poses) / .imu_loss(imu_drots, imu_dvels)           pvgo.py:67-78 / 95-111
+        .align_to(target, idx=0)                                           pvgo.py:114-119
+    run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels,
+             device='cuda:0', radius=1e4, loss_weight=(1,1,1,1), reproj=None, target='vo')   pvgo.py:122-205
+
+The reference builds a dense PyPose LM problem per call; here the graph structure (links) is analysed once and
+cached, the information matrices collapse to the four scalars they are made of (pvgo.py:125-129), and the whole
+`while scheduler.continual()` loop (pvgo.py:177-180) runs on the device.  There is no CPU path.
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+from ._lib import IslamError
+from .solver import PVGOSolver
+
+_SOLVER_CACHE = {}
+_CACHE_MAX = 8
+
+
+def _plain(t):
+    """LieTensor / Tensor / array -> plain torch.Tensor (keeps autograd history)."""
+    if isinstance(t, torch.Tensor):
+        return t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+    return torch.as_tensor(np.asarray(t))
+
+
+def _wrap_like(ref, data, ltype_name):
+    """Re-wrap as a LieTensor when the compat shim is loaded and the caller handed us LieTensors."""
+    try:
+        from . import pypose_compat as pp
+    except Exception:      # pragma: no cover
+        return data
+    if isinstance(ref, pp.LieTensor):
+        return pp.LieTensor(data, ltype=getattr(pp, ltype_name))
+    return data
+
+
+def get_solver(N, links, device):
+    links_np = np.ascontiguousarray(_plain(links).detach().cpu().numpy(), dtype=np.int64).reshape(-1, 2)
+    dev = torch.device(device)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    key = (int(N), str(dev), hashlib.blake2b(links_np.tobytes(), digest_size=16).hexdigest())
+    s = _SOLVER_CACHE.get(key)
+    if s is None:
+        if len(_SOLVER_CACHE) >= _CACHE_MAX:
+            _SOLVER_CACHE.pop(next(iter(_SOLVER_CACHE)))
+        s = PVGOSolver(N, links_np, device=dev)
+        _SOLVER_CACHE[key] = s
+    return s
+
+
+class _VoLoss(torch.autograd.Function):
+    """vo_loss (pvgo.py:67-78): e = Log(P^-1 n1^-1 n2) with the nodes detached; autograd only reaches P.
+    The gradient is returned the way PyPose's LieTensor backward does: left-tangent (6) padded to the 7-slot
+    embedding, so upstream LieTensor ops (train.py:215) keep working."""
+
+    @staticmethod
+    def forward(ctx, P, solver):
+        tl, rl, gt, gr = solver.vo_loss(P, with_grad=True)
+        ctx.save_for_backward(gt, gr)
+        ctx.dev = P.device
+        return tl, rl
+
+    @staticmethod
+    def backward(ctx, g_tl, g_rl):
+        gt, gr = ctx.saved_tensors
+        g = g_tl.to(gt.device).unsqueeze(-1) * gt + g_rl.to(gr.device).unsqueeze(-1) * gr
+        g = torch.cat([g, torch.zeros_like(g[:, :1])], dim=1)
+        return g.to(ctx.dev), None
+
+
+class PoseVelGraph(torch.nn.Module):
+    """pvgo.py:15-119.  Parameters live in the solver handle on the GPU (float32, as the reference)."""
+
+    def __init__(self, nodes, vels, reproj=None, links=None, device='cuda:0'):
+        super().__init__()
+        if reproj is not None:
+            raise NotImplementedError('the optional reprojection factor (pvgo.py:53-61) is not on the B200 path yet')
+        nodes_t, vels_t = _plain(nodes).detach(), _plain(vels).detach()
+        assert nodes_t.size(0) == vels_t.size(0)                              # pvgo.py:19
+        self._device = torch.device(device)
+        self._init = (nodes_t, vels_t)
+        self._nodes_ref = nodes
+        self.solver = None
+        self._problem_key = None
+        if links is not None:
+            self._bind(links)
+
+    def _bind(self, links):
+        self.solver = get_solver(self._init[0].size(0), links, self._device)
+        self.solver.set_state(*self._init)
+
+    def _ensure(self, edges, poses, imu_drots, imu_dtrans, imu_dvels, dts, loss_weight=None):
+        if self.solver is None:
+            self._bind(edges)
+        if loss_weight is not None or self._problem_key is None:
+            lw = (1, 1, 1, 1) if loss_weight is None else loss_weight
+            self.solver.set_problem(_plain(poses), _plain(imu_drots), _plain(imu_dtrans), _plain(imu_dvels),
+                                    _plain(dts).reshape(-1), lw)
+            self._problem_key = tuple(float(x) for x in lw)
+
+    @property
+    def nodes(self):
+        n, _ = self.solver.get_state()
+        return _wrap_like(self._nodes_ref, n, 'SE3_type')
+
+    @property
+    def vels(self):
+        return self.solver.get_state()[1]
+
+    def forward(self, edges, poses, imu_drots, imu_dtrans, imu_dvels, dts):
+        """Returns (pgerr, adjvelerr, imuroterr, transvelerr) — pvgo.py:64."""
+        self._ensure(edges, poses, imu_drots, imu_dtrans, imu_dvels, dts)
+        self.solver.linearize()
+        return self.solver.residuals()
+
+    def vo_loss(self, edges, poses):
+        P = _plain(poses)
+        if P.requires_grad:
+            return _VoLoss.apply(P, self.solver)
+        return self.solver.vo_loss(P)
+
+    def imu_loss(self, imu_drots=None, imu_dvels=None):
+        return self.solver.imu_loss()
+
+    def align_to(self, target, idx=0):
+        if idx != 0:
+            raise NotImplementedError('align_to is only used with idx=0 (pvgo.py:195)')
+        n, v = self.solver.align(_plain(target).detach().reshape(7))
+        return _wrap_like(self._nodes_ref, n, 'SE3_type'), v
+
+
+def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels,
+             device='cuda:0', radius=1e4, loss_weight=(1, 1, 1, 1), reproj=None, target='vo',
+             max_steps=10, patience=3, decreasing=1e-3, use_scheduler=True):
+    """pvgo.py:122-205.  Returns (trans_loss, rot_loss, nodes [cpu, detached], vels [cpu, detached], covs)."""
+    if not torch.cuda.is_available():
+        raise IslamError('run_pvgo needs a CUDA device: there is no CPU fallback')
+    n_links, n_nodes = len(links), len(init_nodes)
+    # pvgo.py:125-131 — the information "matrices" are diagonal with these scalars
+    vo_rot_infos = np.ones(n_links) * loss_weight[0] ** 2
+    vo_trans_infos = np.ones(n_links) * loss_weight[0] ** 2
+    imu_rot_infos = np.ones(n_nodes - 1) * loss_weight[2] ** 2
+    imu_vel_infos = np.ones(n_nodes - 1) * loss_weight[1] ** 2
+    transvel_infos = np.ones(n_nodes - 1) * loss_weight[3] ** 2
+
+    graph = PoseVelGraph(init_nodes, init_vels, reproj, links=links, device=device)
+    graph._ensure(links, _plain(vo_motions).detach(), imu_drots, imu_dtrans, imu_dvels, dts, loss_weight)
+    s = graph.solver
+    # pvgo.py:169-180: LM(min=1e-4) + Cholesky + TrustRegion(radius) + StopOnPlateau(steps=10, patience=3, 1e-3)
+    s.lm_reset(radius=float(radius), lm_min=1e-4, max_steps=int(max_steps), patience=int(patience),
+               decreasing=float(decreasing), use_scheduler=1 if use_scheduler else 0)
+    st = s.lm_run()
+    if st.info:
+        print('Linear solver failed. Breaking optimization step...')            # PyPose's message (A.4)
+
+    if target == 'vo':                                                          # pvgo.py:186-189
+        trans_loss, rot_loss = graph.vo_loss(links, vo_motions)
+    elif target == 'imu':
+        trans_loss, rot_loss = graph.imu_loss(imu_drots, imu_dvels)
+    else:
+        raise ValueError(f'unknown target {target!r}')
+
+    nodes, vels = graph.align_to(_plain(init_nodes)[0])                         # pvgo.py:195
+    nodes = _wrap_like(init_nodes, _plain(nodes).detach().cpu(), 'SE3_type')
+    vels = vels.detach().cpu()
+    covs = {'vo_rot': vo_rot_infos, 'imu_rot': imu_rot_infos, 'vo_trans': vo_trans_infos,
+            'imu_vel': imu_vel_infos, 'transvel': transvel_infos}               # pvgo.py:199-203
+    run_pvgo.last_state = st
+    return trans_loss, rot_loss, nodes, vels, covs

@@ -154,6 +154,13 @@ class PVGOSolver:
         _lib.check(self.L.islam_pvgo_lm_run(self._h, C.byref(st), self._s()), 'islam_pvgo_lm_run')
         return st
 
+    def profile_try(self):
+        """One try with CUDA events between its phases -> dict of milliseconds."""
+        ms = (C.c_float * 5)()
+        self._enter()
+        _lib.check(self.L.islam_pvgo_profile_try(self._h, C.byref(ms), self._s()), 'islam_pvgo_profile_try')
+        return dict(linearize=ms[0], factor=ms[1], backsolve=ms[2], trial=ms[3], total=ms[4])
+
     def lm_try_async(self):
         _lib.check(self.L.islam_pvgo_lm_try(self._h, self._s()), 'islam_pvgo_lm_try')
 

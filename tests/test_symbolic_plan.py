@@ -1,0 +1,77 @@
+"""Host logic: the C++ symbolic analysis (ordering, elimination tree, gather maps) validated by a NumPy emulation of the
+multifrontal numeric phase against a dense solve — no GPU needed."""
+import numpy as np
+import pytest
+
+import mf_emul
+from islam_b200 import synth
+from oracle import pvgo_oracle as po
+
+CASES = {
+    'C1': lambda: synth.config1(),
+    'band8': lambda: synth.config2(N=300, band=8),
+    'band3_odd': lambda: synth.config2(N=57, band=3),
+    'chain': lambda: synth.config3(N=131),
+    'loop_closures': lambda: synth.config4(N=400, n_lc=6, min_gap=50),
+    'window9': lambda: synth.window(),
+    'two_nodes': lambda: synth.window(N=2),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+@pytest.mark.parametrize('opts', [{}, {'leaf_max': 3, 'pivot_max': 2}, {'n_parts': 4}])
+def test_plan_solves_like_dense(name, opts):
+    g = CASES[name]()
+    lm = po.SparseLM(g, np.float64)
+    H, gg, _, _ = lm.assemble(lm._res())
+    H = H.toarray()
+    plan = mf_emul.get_plan(g.N, g.links, **opts)
+    # every pose is a pivot exactly once; parents come later; levels respect the tree
+    assert sorted(np.concatenate([plan['f_nodes'][plan['f_nodes_off'][f]:plan['f_nodes_off'][f] + plan['f_np'][f]]
+                                  for f in range(len(plan['f_np']))]).tolist()) == list(range(g.N))
+    par = plan['f_parent']
+    assert all(p == -1 or p > f for f, p in enumerate(par))
+    assert all(p == -1 or plan['f_level'][p] > plan['f_level'][f] for f, p in enumerate(par))
+    Hd, Ho = mf_emul.blocks_from_dense(H, plan, g.N)
+    scale = 1.0 + 1e-4
+    D = mf_emul.solve(plan, Hd, Ho, gg, scale)
+    A = H.copy()
+    d = np.clip(np.diag(A), 1e-4, 1e32) * scale
+    A[np.arange(len(d)), np.arange(len(d))] = d
+    Dref = np.linalg.solve(A, -gg.reshape(-1)).reshape(-1, 9)
+    assert np.abs(D - Dref).max() <= 1e-9 * np.abs(Dref).max()
+
+
+def test_multi_window_partition_is_consistent():
+    g = synth.config2(N=600, band=8)
+    plan = mf_emul.get_plan(g.N, g.links, n_parts=4)
+    part = plan['f_part']
+    assert set(part.tolist()) == {-1, 0, 1, 2, 3}
+    # private fronts only see poses of their own window or shared poses
+    node_part = part[plan['node_front']]
+    for f in range(len(part)):
+        if part[f] < 0:
+            continue
+        nodes = plan['f_nodes'][plan['f_nodes_off'][f]:plan['f_nodes_off'][f + 1]]
+        assert set(node_part[nodes].tolist()) <= {-1, int(part[f])}
+    # shared fronts' ancestors are shared
+    for f, p in enumerate(plan['f_parent']):
+        if part[f] < 0 and p >= 0:
+            assert part[p] < 0
+    # windows are contiguous index ranges
+    for w in range(4):
+        idx = np.where(node_part == w)[0]
+        shared_between = node_part[idx.min():idx.max() + 1]
+        assert set(shared_between.tolist()) <= {w, -1}
+
+
+def test_invalid_graphs_are_rejected():
+    import ctypes as C
+    from islam_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    bad = np.array([[0, 5]], dtype=np.int64)
+    assert L.islam_plan_build(C.byref(h), 3, 1, bad.ctypes.data, None) < 0          # endpoint out of range
+    self_loop = np.array([[1, 1]], dtype=np.int64)
+    assert L.islam_plan_build(C.byref(h), 3, 1, self_loop.ctypes.data, None) < 0
+    assert L.islam_plan_build(C.byref(h), 1, 0, None, None) < 0                      # fewer than two poses
