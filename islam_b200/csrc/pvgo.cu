@@ -171,7 +171,7 @@ struct islam_pvgo {
     LMState* st_host = nullptr;     // pinned mirror
     int nblk_vo = 0, nblk_imu = 0;
     int max_smem_doubles = 0;
-    std::vector<int> level_smem_doubles, level_bs_bytes;
+    std::vector<int> level_smem_doubles, level_bs_bytes, level_fast;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
     std::vector<int> level_nlocal;
     std::vector<long long> h_shared_off;
@@ -314,18 +314,22 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     h->max_smem_doubles = (max_optin - 1024) / 8;
     cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
     cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
+    cudaFuncSetAttribute(k_factor_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
     h->level_smem_doubles.assign(p.n_levels, 96);
     h->level_bs_bytes.assign(p.n_levels, 0);
+    h->level_fast.assign(p.n_levels, 1);
     for (int f = 0; f < p.F; ++f) {
         int l = p.f_level[f];
         long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
         int nch = p.f_child_off[f + 1] - p.f_child_off[f];
         long long meta = front_meta_doubles(p.f_np[f], p.f_np[f] + p.f_nb[f], nch);
-        long long need = Rf * Cf + 96 + meta;
+        long long need = ((Rf + 3) & ~3LL) * Cf + 96 + meta;
+        if (need > h->max_smem_doubles || meta == 0) h->level_fast[l] = 0;   // this level takes the generic kernel
         if (need > h->max_smem_doubles) need = 96 + meta;        // panel stays in global memory
         if (need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;
-        long long bs = (Rb + Cf + 16) * 8;
-        if (bs > max_optin - 1024) { delete h; return -5; }       // boundary too wide for the back-substitution kernel
+        long long bs_min = (Rb + Cf + 16 + 81LL * p.f_np[f]) * 8, bs = bs_min + Rf * Cf * 8;
+        if (bs_min > max_optin - 1024) { delete h; return -5; }   // boundary too wide for the back-substitution kernel
+        if (bs > max_optin - 1024) bs = bs_min;                   // panel read straight from global memory
         if (bs > h->level_bs_bytes[l]) h->level_bs_bytes[l] = (int)bs;
     }
     // views
@@ -433,10 +437,16 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int
         int b = p.level_off[l];
         int nloc = h->level_nlocal[l];
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
-        if (which == 0 && nloc > 0)
-            k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
-                                                          h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
-                                                          forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail);
+        if (which == 0 && nloc > 0) {
+            if (h->level_fast[l])
+                k_factor_fast<<<nloc, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
+                                                            h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min,
+                                                            q.lm_max, forced_scale, 0, &h->st.p->chol_fail);
+            else
+                k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
+                                                              h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
+                                                              forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail);
+        }
     }
     return (int)cudaGetLastError();
 }
@@ -459,9 +469,14 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
         if (!ns) continue;
         int b = p.level_off[l] + h->level_nlocal[l];
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
-        k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
-                                                    h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
-                                                    h->level_smem_doubles[l], 2, &h->st.p->chol_fail);
+        if (h->level_fast[l])
+            k_factor_fast<<<ns, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
+                                                      h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
+                                                      forced_scale, 2, &h->st.p->chol_fail);
+        else
+            k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
+                                                        h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
+                                                        h->level_smem_doubles[l], 2, &h->st.p->chol_fail);
     }
     return (int)cudaGetLastError();
 }
@@ -471,8 +486,9 @@ static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     for (int l = p.n_levels - 1; l >= 0; --l) {
         int n = h->level_nlocal[l] + level_nshared(h, l);
         if (!n) continue;
-        k_backsolve_level<<<n, BS_THREADS, (size_t)h->level_bs_bytes[l], s>>>(h->st.p, h->d_level_fronts.p + p.level_off[l],
-                                                                              h->fm, h->Lbuf.p, h->Linv.p, h->D.p, force);
+        k_backsolve_level<<<n, BS_THREADS2, (size_t)h->level_bs_bytes[l], s>>>(h->st.p, h->d_level_fronts.p + p.level_off[l],
+                                                                               h->fm, h->Lbuf.p, h->Linv.p, h->D.p, force,
+                                                                               h->level_bs_bytes[l] / 8);
     }
     return (int)cudaGetLastError();
 }
@@ -771,3 +787,11 @@ extern "C" int64_t islam_plan_array(const islam_plan* pl, const char* name, cons
 #undef ARR
     return -1;
 }
+
+#ifdef ISLAM_PHASE_CLOCKS
+extern "C" int islam_debug_phase_grid(int g) { return (int)cudaMemcpyToSymbol(islam::g_phase_grid, &g, sizeof(int)); }
+extern "C" int islam_debug_phase_clocks(long long* out64) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out64, islam::g_phase_clk, sizeof(long long) * 64);
+}
+#endif

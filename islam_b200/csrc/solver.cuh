@@ -88,7 +88,7 @@ __device__ __forceinline__ bool chol9(const double* __restrict__ Dblk, double* L
 // ---- per-front metadata staged in shared memory -------------------------------------------------------------
 // The gathers below touch the maps once per matrix element; chasing them through L2 (5-6 dependent loads per
 // element) made a single front cost ~240 us, so a CTA copies everything it needs into shared memory first.
-constexpr int MAXC = 6;      // children handled on the fast path (more => generic global-memory path)
+constexpr int MAXC = 4;      // children handled on the fast path (more => generic global-memory path)
 constexpr int MAXS = 40;     // slots (pivot + boundary poses) handled on the fast path
 
 struct FrontCtx {
@@ -105,7 +105,7 @@ struct FrontCtx {
 __host__ __device__ __forceinline__ int front_meta_doubles(int np, int ns, int nch) {
     if (nch > MAXC || ns > MAXS) return 0;
     int ints = 2 * MAXC /* long long offsets */ + ns + ns * np + nch * ns + 2 * nch;
-    return (ints + 1) / 2 + 1;
+    return (((ints + 1) / 2 + 1) + 1) & ~1;       // even: the panel behind it stays 16-byte aligned
 }
 
 __device__ __forceinline__ void stage_front(const FrontMeta& m, int f, int* si, FrontCtx& c) {
@@ -357,6 +357,368 @@ k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, F
     }
 }
 
+// ---- fast path: one CTA of 512 threads per front, everything block-structured ------------------------------------
+// Used when every front of a level fits the shared-memory budget with <= MAXC children and <= MAXS slots (always
+// the case for chain / band graphs; fronts that do not qualify take k_factor_level above).
+constexpr int F3_THREADS = 512;
+#ifdef ISLAM_PHASE_CLOCKS
+__device__ long long g_phase_clk[64];
+__device__ int g_phase_grid = 1;
+#define PHASE(n) do { if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
+#else
+#define PHASE(n) do { } while (0)
+#endif
+
+// right-looking 9x9 Cholesky in registers (packed lower A -> L), reciprocal diagonal in linv
+__device__ __forceinline__ bool chol9_rl(double* A, double* linv) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        double d = A[c * (c + 1) / 2 + c];
+        if (!(d > 0.0) || !(d < 1e300)) { ok = false; d = 1.0; }
+        double inv = rsqrt(d);
+        inv = inv * (1.5 - 0.5 * d * inv * inv);             // one Newton step: full double accuracy
+        linv[c] = inv;
+        A[c * (c + 1) / 2 + c] = d * inv;
+#pragma unroll
+        for (int r = c + 1; r < 9; ++r) A[r * (r + 1) / 2 + c] *= inv;
+#pragma unroll
+        for (int r = c + 1; r < 9; ++r)
+#pragma unroll
+            for (int c2 = c + 1; c2 <= r; ++c2) A[r * (r + 1) / 2 + c2] -= A[r * (r + 1) / 2 + c] * A[c2 * (c2 + 1) / 2 + c];
+    }
+    return ok;
+}
+
+// column `lane` (< 9) of the inverse of the packed lower-triangular L, branch-free: entries above the diagonal
+// come out as exact zeros because the partial sums only ever see zeros there
+__device__ __forceinline__ void tri_inv_col_uniform(const double* L, const double* linv, int col, double* x) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) s += L[i * (i + 1) / 2 + k] * x[k];
+        x[i] = (i == col) ? linv[i] : -s * linv[i];
+        if (i < col) x[i] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
+              const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
+              double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
+              const double* __restrict__ shared, double lm_min, double lm_max, double forced_scale, int stage,
+              int* chol_fail) {
+    if (forced_scale == 0.0 && !st->active) return;
+    const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+    const int f = fronts[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = F3_THREADS / 32;
+    PHASE(0);
+    extern __shared__ double smem[];
+    double* sLinv = smem;                      // 81 (+ pad to 96)
+    FrontCtx c;
+    stage_front(m, f, (int*)(smem + 96), c);
+    const int np = c.np, nb = c.nb, ns = c.ns;
+    const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ub = Rb + 1;
+    const int ld = (Rf + 3) & ~3;              // 32-byte aligned columns: LDS.128 on row quads
+    double* P = smem + 96 + front_meta_doubles(np, ns, c.nch);
+    double* Lg = Lbuf + m.Loff[f];
+    double* Ug = Ubuf + m.Uoff[f];
+    const double* base = (stage == 2) ? shared + m.shared_off[f] : nullptr;
+    __syncthreads();
+    PHASE(1);
+
+    // A. assembly, one warp per 9x9 block (row block rs in [cs, ns]; rs == ns is the rhs row); two blocks are in
+    // flight per warp so that their (DRAM-latency) gathers overlap
+    {
+        int ea[3], eb[3];                      // this lane's (row, col) inside a 9x9 block, row fastest
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { int e = lane + 32 * j; eb[j] = e / 9; ea[j] = e - 9 * eb[j]; }
+        int nblk = 0;
+        for (int cs = 0; cs < np; ++cs) nblk += ns + 1 - cs;
+        for (int blk0 = warp; blk0 < nblk; blk0 += 2 * NW) {
+            double v[2][3], tv[2][MAXC][3];
+            int i0s[2], j0s[2];
+            bool rhss[2], valid[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int blk = blk0 + u * NW;
+                valid[u] = blk < nblk;
+                int cs = 0, rem = valid[u] ? blk : 0;
+                while (rem >= ns + 1 - cs) { rem -= ns + 1 - cs; ++cs; }
+                const int rs = cs + rem;
+                const bool rhs = (rs == ns);
+                const int nc = c.nodes[cs];
+                const int i0 = rhs ? Rf - 1 : 9 * rs, j0 = 9 * cs;
+                i0s[u] = i0; j0s[u] = j0; rhss[u] = rhs;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[u][j] = 0.0;
+                if (stage == 2) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        int e = lane + 32 * j;
+                        if (e < (rhs ? 9 : 81)) {
+                            int a = rhs ? 0 : ea[j], b = rhs ? e : eb[j];
+                            v[u][j] = base[(i0 + a) + (long long)(j0 + b) * Rf];
+                            if (i0 + a == j0 + b) v[u][j] += fmin(fmax(base[(long long)Rf * Rf + j0 + b], lm_min), lm_max) * scale;
+                        }
+                    }
+                } else if (rhs) {
+                    if (lane < 9) v[u][0] = -g[9 * (size_t)nc + lane];
+                } else if (rs == cs) {
+                    const double* ob = Hd + 81 * (size_t)nc;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (lane + 32 * j < 81) {
+                            double t = ob[9 * ea[j] + eb[j]];
+                            v[u][j] = (ea[j] == eb[j]) ? fmin(fmax(t, lm_min), lm_max) * scale : t;
+                        }
+                } else {
+                    int h = c.hmap[rs * np + cs];
+                    if (h >= 0) {
+                        const double* ob = Ho + 81 * (size_t)(h >> 1);
+                        const bool tr = h & 1;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            if (lane + 32 * j < 81) v[u][j] = tr ? ob[9 * eb[j] + ea[j]] : ob[9 * ea[j] + eb[j]];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) {
+                    const double* up = nullptr;
+                    int uld = 0;
+                    if (k < c.nch && !(stage == 2 && !c.cshared[k])) {
+                        const int* inv = c.inv + k * ns;
+                        const int cc = inv[cs], nbc = c.cnb[k];
+                        const int rc = rhs ? 9 * nbc : (inv[rs] >= 0 ? 9 * inv[rs] : -1);
+                        if (cc >= 0 && rc >= 0) { uld = 9 * nbc + 1; up = Ubuf + c.cU[k] + rc + (long long)(9 * cc) * uld; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        tv[u][k][j] = 0.0;
+                        if (up != nullptr) {
+                            if (rhs) { if (j == 0 && lane < 9) tv[u][k][0] = up[(long long)lane * uld]; }
+                            else if (lane + 32 * j < 81) tv[u][k][j] = up[ea[j] + eb[j] * uld];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!valid[u]) continue;
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) v[u][j] += tv[u][k][j];
+                if (rhss[u]) { if (lane < 9) P[i0s[u] + (j0s[u] + lane) * ld] = v[u][0]; }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (lane + 32 * j < 81) P[(i0s[u] + ea[j]) + (j0s[u] + eb[j]) * ld] = v[u][j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    PHASE(2);
+
+    // B. right-looking blocked Cholesky of the panel
+    bool ok = true;
+    for (int jb = 0; jb < np; ++jb) {
+        const int c0 = 9 * jb;
+        if (warp == 0) {                                     // 1. diagonal block: factor + invert (registers)
+            double A[45], linv[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r)
+#pragma unroll
+                for (int q = 0; q <= r; ++q) A[r * (r + 1) / 2 + q] = P[(c0 + r) + (c0 + q) * ld];
+            ok = chol9_rl(A, linv) && ok;
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 9; ++r)
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) P[(c0 + r) + (c0 + q) * ld] = (q <= r) ? A[r * (r + 1) / 2 + (q <= r ? q : 0)] : 0.0;
+            }
+            if (lane < 9) {
+                double x[9];
+                tri_inv_col_uniform(A, linv, lane, x);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) sLinv[9 * i + lane] = x[i];
+            }
+        }
+        __syncthreads();
+        PHASE(10 + 3 * jb);
+        if (tid < 81) Linv[81 * (size_t)c.nodes[jb] + tid] = sLinv[tid];
+        // 2. rows below the diagonal block: x = Lkk^-1 applied from the right
+        for (int i = c0 + 9 + tid; i < Rf; i += F3_THREADS) {
+            double acc[9], x[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) acc[q] = P[i + (c0 + q) * ld];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                double s_ = 0.0;
+#pragma unroll
+                for (int k = 0; k <= q; ++k) s_ += acc[k] * sLinv[9 * q + k];
+                x[q] = s_;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) P[i + (c0 + q) * ld] = x[q];
+        }
+        __syncthreads();
+        PHASE(11 + 3 * jb);
+        // 3. trailing update of the later block columns: 4-row x 9-column register tiles
+        const int ncb = np - 1 - jb;
+        if (ncb > 0) {
+            // column block cb only needs rows >= 9 cb (lower trapezoid): its own row-tile count S_cb
+            int tasks = 0;
+            for (int cb = jb + 1; cb < np; ++cb) tasks += (Rf - 9 * cb + 3) >> 2;
+            for (int t = tid; t < tasks; t += F3_THREADS) {
+                int cb = jb + 1, rt = t;
+                while (rt >= ((Rf - 9 * cb + 3) >> 2)) { rt -= (Rf - 9 * cb + 3) >> 2; ++cb; }
+                const int j0 = 9 * cb, S = (Rf - j0 + 3) >> 2;
+                int ix[4];
+                bool vx[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { ix[x] = j0 + rt + x * S; vx[x] = ix[x] < Rf; if (!vx[x]) ix[x] = j0; }
+                double acc[4][9];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 9; ++y) acc[x][y] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const double* col = P + (c0 + q) * ld;
+                    double av[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
+#pragma unroll
+                    for (int y = 0; y < 9; ++y) {
+                        double bv = col[j0 + y];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) acc[x][y] += av[x] * bv;
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (vx[x])
+#pragma unroll
+                        for (int y = 0; y < 9; ++y) P[ix[x] + (j0 + y) * ld] -= acc[x][y];
+            }
+        }
+        __syncthreads();
+        PHASE(12 + 3 * jb);
+    }
+    if (!ok && tid == 0) *chol_fail = 1;
+    PHASE(3);
+
+    // C. keep the factor for the back-substitution (global panel has leading dimension Rf)
+    for (int idx = tid; idx < Rf * Cf; idx += F3_THREADS) {
+        int j = idx / Rf, i = idx - j * Rf;
+        Lg[idx] = P[i + j * ld];
+    }
+
+    __syncthreads();
+    PHASE(4);
+    // D. update matrix on the boundary (+ rhs row): U = pass-through - L21 L21^T.
+    // 4x4 register tiles over the lower triangle; operands are LDS.128 pairs (columns of the panel are 32-byte aligned).
+    if (ub > 1) {
+        const double* L21 = P + Cf;              // Cf = 9 np; row quads are 32-byte aligned when Cf % 4 == 0
+        const int ntr = (ub + 3) >> 2;           // 4-row / 4-column tiles
+        // thread tiles flattened over the lower triangle, row tile major: lanes of a warp share the row operand
+        const int ntiles = ntr * (ntr + 1) / 2;
+        for (int t = tid; t < ntiles; t += F3_THREADS) {
+            int tr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+            while (tr * (tr + 1) / 2 > t) --tr;
+            const int tc = t - tr * (tr + 1) / 2;
+            const bool active = true;
+            const int r0 = 4 * tr, s0 = 4 * tc;
+            double acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+            const bool full = (r0 + 3 < ub) && (s0 + 3 < ub) && ((Cf & 3) == 0);
+            if (full) {
+                const double* pa = L21 + r0;
+                const double* pb = L21 + s0;
+#pragma unroll 4
+                for (int k = 0; k < Cf; ++k) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(pa + k * ld);
+                    const double2 a23 = *reinterpret_cast<const double2*>(pa + k * ld + 2);
+                    const double2 b01 = *reinterpret_cast<const double2*>(pb + k * ld);
+                    const double2 b23 = *reinterpret_cast<const double2*>(pb + k * ld + 2);
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+                }
+            } else {
+                int ri[4], si[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { ri[q] = min(r0 + q, ub - 1); si[q] = min(s0 + q, ub - 1); }
+                for (int k = 0; k < Cf; ++k) {
+                    const double* col = L21 + k * ld;
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { av[q] = col[ri[q]]; bv[q] = col[si[q]]; }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+                }
+            }
+            if (!active) continue;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = -acc[x][y];
+            if (stage == 2) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        int r = r0 + x, s_ = s0 + y;
+                        if (r < ub && s_ < ub && r >= s_) acc[x][y] += base[(Cf + r) + (long long)(Cf + s_) * Rf];
+                    }
+            }
+            for (int k = 0; k < c.nch; ++k) {
+                if (stage == 2 && !c.cshared[k]) continue;
+                const int* inv = c.inv + k * ns;
+                const int nbc = c.cnb[k], ldu = 9 * nbc + 1;
+                const double* Uc = Ubuf + c.cU[k];
+                int rc[4], cc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int r = r0 + q, s_ = s0 + q;
+                    if (r >= ub) rc[q] = -1;
+                    else if (r == ub - 1) rc[q] = 9 * nbc;
+                    else { int t2 = inv[np + r / 9]; rc[q] = t2 >= 0 ? 9 * t2 + r % 9 : -1; }
+                    if (s_ >= ub - 1) cc[q] = -1;
+                    else { int t2 = inv[np + s_ / 9]; cc[q] = t2 >= 0 ? 9 * t2 + s_ % 9 : -1; }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        if (rc[x] >= 0 && cc[y] >= 0 && rc[x] >= cc[y]) acc[x][y] += Uc[rc[x] + (long long)cc[y] * ldu];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    int r = r0 + x, s_ = s0 + y;
+                    if (r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1)) Ug[r + (long long)s_ * ub] = acc[x][y];
+                }
+        }
+    }
+    __syncthreads();
+    PHASE(5);
+}
+
 // ---- multi-GPU: pre-all-reduce base of the shared fronts ------------------------------------------------
 // Per shared front: Rf x Rf column-major partial sums (original entries of the factors this rank owns + update
 // matrices of its private children) followed by the 9np partial ORIGINAL pivot diagonals, kept apart because
@@ -392,12 +754,17 @@ k_shared_base(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
 // ---- back-substitution of one level (root first) --------------------------------------------------------
 // x_p = L11^-T (y_p - L21^T x_b), blocked by pose: the inverse 9x9 diagonal blocks were stored by the factor
 // kernel, so every block step is a 9x9 mat-vec followed by a 9-deep update of the earlier unknowns.
-__global__ void __launch_bounds__(BS_THREADS)
+// The whole panel is pulled into shared memory with one burst of independent loads first: the factor was written a
+// few hundred MB of traffic ago, so every access is a DRAM-latency access and must not sit on a dependent chain.
+constexpr int BS_THREADS2 = 512;
+__global__ void __launch_bounds__(BS_THREADS2)
 k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
-                  const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force) {
+                  const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force,
+                  int smem_doubles) {
     if (!force && !st->active) return;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = BS_THREADS2 / 32;
     extern __shared__ double smem[];
     const int np = m.np[f], nb = m.nb[f];
     const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ld = Rf;
@@ -405,15 +772,19 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
     const double* Lg = Lbuf + m.Loff[f];
     double* xb = smem;                 // [Rb]
     double* ts = xb + Rb;              // [Cf]
-    double* xs = ts + Cf;              // [9] current block solution
-    for (int r = tid; r < Rb; r += BS_THREADS) {
-        int slot = np + r / 9;
-        xb[r] = D[9 * (size_t)nodes[slot] + (r % 9)];
-    }
+    double* xs = ts + Cf;              // [16]
+    double* sLi = xs + 16;             // [np][81] inverse diagonal blocks
+    double* sP = sLi + 81 * np;        // [Rf x Cf] panel copy (if it fits)
+    const bool staged = (Rb + Cf + 16 + 81 * np + Rf * Cf <= smem_doubles);
+    for (int r = tid; r < Rb; r += BS_THREADS2) xb[r] = D[9 * (size_t)nodes[np + r / 9] + (r % 9)];
+    for (int i = tid; i < 81 * np; i += BS_THREADS2) sLi[i] = Linv[81 * (size_t)nodes[i / 81] + (i % 81)];
+    if (staged)
+        for (int i = tid; i < Rf * Cf; i += BS_THREADS2) sP[i] = Lg[i];
+    const double* Lp = staged ? sP : Lg;
     __syncthreads();
-    // ts[c] = y[c] - sum_r L21[r,c] xb[r]      (one warp per column, coalesced)
-    for (int c = w; c < Cf; c += BS_THREADS / 32) {
-        const double* col = Lg + (long long)c * ld + Cf;
+    // ts[c] = y[c] - sum_r L21[r,c] xb[r]      (one warp per column)
+    for (int c = w; c < Cf; c += NW) {
+        const double* col = Lp + c * ld + Cf;
         double s = 0.0;
         for (int r = lane; r < Rb; r += 32) s += col[r] * xb[r];
         s = warp_sum(s);
@@ -423,7 +794,7 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
     for (int jb = np - 1; jb >= 0; --jb) {
         const int c0 = 9 * jb;
         if (tid < 9) {                             // x_blk = Lkk^-T ts_blk :  x[a] = sum_{b>=a} Linv[b][a] ts[b]
-            const double* Li = Linv + 81 * (size_t)nodes[jb];
+            const double* Li = sLi + 81 * jb;
             double s = 0.0;
 #pragma unroll
             for (int b = 0; b < 9; ++b) s += (b >= tid) ? Li[9 * b + tid] * ts[c0 + b] : 0.0;
@@ -431,8 +802,8 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
         }
         __syncthreads();
         if (tid < 9) ts[c0 + tid] = xs[tid];
-        for (int k = tid; k < c0; k += BS_THREADS) {   // ts[k] -= sum_{c in blk} L[c,k] x[c]   (column k, rows c0..c0+8)
-            const double* col = Lg + (long long)k * ld + c0;
+        for (int k = tid; k < c0; k += BS_THREADS2) {   // ts[k] -= sum_{c in blk} L[c,k] x[c]   (column k, rows c0..c0+8)
+            const double* col = Lp + k * ld + c0;
             double s = 0.0;
 #pragma unroll
             for (int q = 0; q < 9; ++q) s += col[q] * xs[q];
@@ -440,7 +811,7 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
         }
         __syncthreads();
     }
-    for (int c = tid; c < Cf; c += BS_THREADS) D[9 * (size_t)nodes[c / 9] + (c % 9)] = ts[c];
+    for (int c = tid; c < Cf; c += BS_THREADS2) D[9 * (size_t)nodes[c / 9] + (c % 9)] = ts[c];
 }
 
 }  // namespace islam
