@@ -124,10 +124,23 @@ int islam_pvgo_get_lm_state(islam_pvgo* h, islam_lm_state* out, void* stream); /
 /* one try timed phase by phase with CUDA events on `stream` (ms[5]: linearise, factor, back-substitution,
  * retract + trial loss + control, total); synchronises — measurement aid for bench.py's roofline object */
 int islam_pvgo_profile_try(islam_pvgo* h, float* ms, void* stream);
-/* multi-GPU: a try split around the single all-reduce of the shared (separator) panels */
+/* multi-GPU (n_parts > 1): one try split around the collectives.  Every rank holds the whole (small) state but
+ * linearises only the factors it owns and factors only its window's fronts:
+ *   try_begin : linearise owned factors, factor the private fronts, write the partial panels of the shared
+ *               (separator) fronts + the partial linearisation loss into the shared buffer
+ *   -> all-reduce(SUM) of islam_pvgo_shared_buffer   (the per-try exchange of separator J^T W J / J^T W r blocks)
+ *   try_mid   : factor the shared fronts (redundantly, identical on every rank), back-substitute, retract, evaluate
+ *               the trial residuals of the owned factors -> 2 partial sums
+ *   -> all-reduce(SUM) of islam_pvgo_sums_buffer     (2 doubles: trial sum r^2 and the quality term)
+ *   try_end   : trust-region update + accept / roll back (identical decision on every rank)
+ * With n_parts == 1 the three calls in sequence are exactly islam_pvgo_lm_try. */
 int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream);
 int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
+int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream);
+int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
 int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
+/* owner window of every pose (host array of N int32): >= 0 private to that rank, -1 shared / replicated */
+int islam_pvgo_node_parts(const islam_pvgo* h, int32_t* out_host);
 
 /* ---- outer losses and gauge alignment ------------------------------------------------------------------ */
 /* vo_loss (pvgo.py:67-78) at the current nodes (detached) for arbitrary vo_motions P (E x 7):

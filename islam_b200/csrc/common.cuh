@@ -25,6 +25,7 @@ struct FrontMeta {
     const int* hmap;        // (np+nb) x np : (pair<<1|transpose) | -1
     const int* part;        // [F] owning window or -1 (shared)
     const long long* shared_off;  // [F] offset into the shared all-reduce buffer or -1
+    int mypart;                   // this rank's window (multi-GPU)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

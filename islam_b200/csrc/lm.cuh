@@ -17,23 +17,31 @@ __global__ void k_begin_try(LMState* st) {
     st->tries_total += 1;
 }
 
-// sums the partials of the linearisation pass (fixed order) and opens the step / the try
-__global__ void __launch_bounds__(256) k_begin_step(LMState* st, const double* __restrict__ part, int nparts) {
-    if (!st->active) return;
-    __shared__ double sh[8];
-    if (st->do_lin) {
-        double s = 0.0;
-        for (int k = threadIdx.x; k < nparts; k += 256) s += part[2 * k];
-        s = block_sum<256>(s, sh);
-        if (threadIdx.x == 0) {
-            st->lin_loss = s;
-            if (!st->loss_valid) { st->loss = s; st->loss_valid = 1; }     // first call: loss = model.loss()
-            st->last = st->loss;
-            st->reject_count = 0;
-            st->diag_scale = 1.0;
-        }
-    }
-    if (threadIdx.x == 0) st->diag_scale *= (1.0 + st->damping);          // A.diag += A.diag * damping
+// deterministic sum of per-block partials: out[0] = sum part[2k] (sum r^2), out[1] = sum part[2k+1] (quality term)
+__global__ void __launch_bounds__(256) k_reduce2(const LMState* __restrict__ st, const double* __restrict__ part, int nparts,
+                                                 double* __restrict__ out, int lin_only) {
+    if (!st->active || (lin_only && !st->do_lin)) return;
+    __shared__ double sh[8], sh2[8];
+    double s = 0.0, q = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
+    s = block_sum<256>(s, sh);
+    q = block_sum<256>(q, sh2);
+    if (threadIdx.x == 0) { out[0] = s; out[1] = q; }
+}
+
+// opens the step / the try: cumulative damping of the (clamped) diagonal (A.4)
+__global__ void k_begin_step_a(LMState* st) {
+    if (threadIdx.x != 0 || !st->active) return;
+    if (st->do_lin) { st->reject_count = 0; st->diag_scale = 1.0; }
+    st->diag_scale *= (1.0 + st->damping);                                   // A.diag += A.diag * damping
+}
+
+// after the (possibly all-reduced) linearisation loss is known
+__global__ void k_begin_step_b(LMState* st, const double* __restrict__ lin_sum) {
+    if (threadIdx.x != 0 || !st->active || !st->do_lin) return;
+    st->lin_loss = lin_sum[0];
+    if (!st->loss_valid) { st->loss = lin_sum[0]; st->loss_valid = 1; }      // first call: loss = model.loss()
+    st->last = st->loss;
 }
 
 // nodes <- Exp(d[:6]) nodes ; vels <- vels + d[6:9]   (LieTensor.add_ / update_parameter, A.1/A.4)
@@ -74,15 +82,9 @@ __device__ __forceinline__ void lm_end_step(LMState* st, const islam_lm_params& 
 }
 
 // trial loss + trust-region update + accept / roll back
-__global__ void __launch_bounds__(256)
-k_lm_control(LMState* st, islam_lm_params p, const double* __restrict__ part, int nparts) {
-    if (!st->active) return;
-    __shared__ double sh[8], sh2[8];
-    double s = 0.0, q = 0.0;
-    for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
-    s = block_sum<256>(s, sh);
-    q = block_sum<256>(q, sh2);
-    if (threadIdx.x != 0) return;
+__global__ void k_lm_control(LMState* st, islam_lm_params p, const double* __restrict__ sums) {
+    if (threadIdx.x != 0 || !st->active) return;
+    const double s = sums[0], q = sums[1];
     st->loss_trial = s;
     if (st->chol_fail) {            // "Linear solver failed. Breaking optimization step..." : params untouched
         st->info = 1;

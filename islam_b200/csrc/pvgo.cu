@@ -159,7 +159,7 @@ struct islam_pvgo {
     DevBuf<float> nodes[2], vels[2];
     // linearisation
     DevBuf<float> r_vo, J_vo, r_imu, J_rot;
-    DevBuf<double> S_vo, q_vo, lin_part, trial_part;
+    DevBuf<double> S_vo, q_vo, lin_part, trial_part, sums;
     DevBuf<double> Hd, Ho, g, D;
     // symbolic plan on the device
     DevBuf<int> d_node_eoff, d_node_edges, d_pair_lo, d_pair_hi, d_pair_adj, d_pair_eoff, d_pair_edges;
@@ -191,7 +191,7 @@ struct islam_pvgo {
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot};
         for (auto* b : fb) b->release();
-        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared};
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared};
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_shared_off.release();
         st.release();
@@ -259,6 +259,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     h->nblk_vo = (E + LIN_THREADS - 1) / LIN_THREADS;
     h->nblk_imu = (p.M + LIN_THREADS - 1) / LIN_THREADS;
     AL(lin_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu)); AL(trial_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu));
+    AL(sums, 8);
     AL(Hd, 81 * (size_t)N); AL(Ho, 81 * (size_t)p.P); AL(g, 9 * (size_t)N); AL(D, 9 * (size_t)N);
     UP(d_node_eoff, p.node_eoff); UP(d_node_edges, p.node_edges); UP(d_pair_lo, p.pair_lo); UP(d_pair_hi, p.pair_hi);
     UP(d_pair_adj, p.pair_adj); UP(d_pair_eoff, p.pair_eoff); UP(d_pair_edges, p.pair_edges);
@@ -303,6 +304,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     }
     AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles); AL(Linv, 81 * (size_t)N);
     AL(st, 1);
+    cudaMemset(h->D.p, 0, sizeof(double) * 9 * (size_t)N);
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
 #undef AL
@@ -350,7 +352,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     fm.np = h->d_np.p; fm.nb = h->d_nb.p; fm.nodes_off = h->d_nodes_off.p; fm.nodes = h->d_nodes.p;
     fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.child_off = h->d_child_off.p; fm.children = h->d_children.p;
     fm.cinv_off = h->d_cinv_off.p; fm.cinv = h->d_cinv.p; fm.hmap_off = h->d_hmap_off.p; fm.hmap = h->d_hmap.p;
-    fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p;
+    fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p; fm.mypart = opts.part;
     // LM state
     LMState s;
     std::memset(&s, 0, sizeof(s));
@@ -564,11 +566,19 @@ extern "C" int islam_pvgo_lm_reset(islam_pvgo* h, const islam_lm_params* p, void
     return 0;
 }
 
+static double* lin_sum_ptr(islam_pvgo* h) {          // single GPU: private scratch; multi-GPU: tail of the all-reduce buffer
+    return h->opts.n_parts > 1 ? h->shared.p + (h->shared_doubles - 4) : h->sums.p;
+}
+static double* trial_sum_ptr(islam_pvgo* h) { return h->sums.p + 4; }
+
 static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
+    const int np_ = h->nblk_vo + h->nblk_imu;
     k_begin_try<<<1, 32, 0, s>>>(h->st.p);
     int rc = launch_linearize(h, s, 0);
     if (rc) return rc;
-    k_begin_step<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, h->nblk_vo + h->nblk_imu);
+    k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, np_, lin_sum_ptr(h), 1);
+    k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
+    if (h->opts.n_parts == 1) k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
     rc = launch_factor(h, s, 0.0, 0);
     if (rc) return rc;
     if (h->opts.n_parts > 1 && h->n_shared > 0) {
@@ -578,10 +588,16 @@ static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
+// after the all-reduce of the shared panels (multi-GPU) / directly (single GPU): finish the solve, evaluate the trial
+static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
     const Plan& p = h->plan;
+    const int np_ = h->nblk_vo + h->nblk_imu;
     int rc = 0;
-    if (h->opts.n_parts > 1) { rc = launch_factor_shared(h, s, 0.0); if (rc) return rc; }
+    if (h->opts.n_parts > 1) {
+        k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
+        rc = launch_factor_shared(h, s, 0.0);
+        if (rc) return rc;
+    }
     rc = launch_backsolve(h, s, 0);
     if (rc) return rc;
     k_retract<<<(p.N + 127) / 128, 128, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->D.p, p.N);
@@ -590,7 +606,12 @@ static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
         k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
     k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
                                                   h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
-    k_lm_control<<<1, 256, 0, s>>>(h->st.p, h->prm, part, h->nblk_vo + h->nblk_imu);
+    k_reduce2<<<1, 256, 0, s>>>(h->st.p, part, np_, trial_sum_ptr(h), 0);
+    return (int)cudaGetLastError();
+}
+
+static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
+    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->prm, trial_sum_ptr(h));
     return (int)cudaGetLastError();
 }
 
@@ -601,13 +622,16 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
     if (h->opts.n_parts > 1) return -6;
     cudaStream_t s = (cudaStream_t)stream;
     const Plan& p = h->plan;
+    const int np_ = h->nblk_vo + h->nblk_imu;
     cudaEvent_t ev[5];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     int rc = 0;
     CK(cudaEventRecord(ev[0], s));
     k_begin_try<<<1, 32, 0, s>>>(h->st.p);
     rc = launch_linearize(h, s, 0);
-    k_begin_step<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, h->nblk_vo + h->nblk_imu);
+    k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, np_, lin_sum_ptr(h), 1);
+    k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
+    k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
     CK(cudaEventRecord(ev[1], s));
     if (!rc) rc = launch_factor(h, s, 0.0, 0);
     CK(cudaEventRecord(ev[2], s));
@@ -619,7 +643,8 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
         k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
     k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
                                                   h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
-    k_lm_control<<<1, 256, 0, s>>>(h->st.p, h->prm, part, h->nblk_vo + h->nblk_imu);
+    k_reduce2<<<1, 256, 0, s>>>(h->st.p, part, np_, trial_sum_ptr(h), 0);
+    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->prm, trial_sum_ptr(h));
     CK(cudaEventRecord(ev[4], s));
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
@@ -631,6 +656,8 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
 
 static int enqueue_try(islam_pvgo* h, cudaStream_t s) {
     int rc = enqueue_try_begin(h, s);
+    if (rc) return rc;
+    rc = enqueue_try_mid(h, s);
     if (rc) return rc;
     return enqueue_try_end(h, s);
 }
@@ -645,6 +672,10 @@ extern "C" int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream) {
     if (!h) return -1;
     return enqueue_try_begin(h, (cudaStream_t)stream);
 }
+extern "C" int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream) {
+    if (!h) return -1;
+    return enqueue_try_mid(h, (cudaStream_t)stream);
+}
 extern "C" int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream) {
     if (!h) return -1;
     return enqueue_try_end(h, (cudaStream_t)stream);
@@ -653,6 +684,19 @@ extern "C" int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t
     if (!h || !dev_ptr || !n) return -1;
     *dev_ptr = h->shared.p;
     *n = h->shared_doubles;
+    return 0;
+}
+extern "C" int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n) {
+    if (!h || !dev_ptr || !n) return -1;
+    *dev_ptr = trial_sum_ptr(h);
+    *n = 2;
+    return 0;
+}
+// owner window of every pose: >= 0 private to that rank, -1 shared (solved redundantly on every rank)
+extern "C" int islam_pvgo_node_parts(const islam_pvgo* h, int32_t* out_host) {
+    if (!h || !out_host) return -1;
+    const Plan& p = h->plan;
+    for (int n = 0; n < p.N; ++n) out_host[n] = p.f_part[p.node_front[n]];
     return 0;
 }
 

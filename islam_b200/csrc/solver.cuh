@@ -26,7 +26,7 @@ __device__ __forceinline__ double pull_children(const FrontMeta& m, const double
     for (int k = k0; k < k1; ++k) {
         int c = m.children[k];
         if (mode == 1 && m.part[c] >= 0) continue;     // shared children only
-        if (mode == 2 && m.part[c] < 0) continue;      // private children only
+        if (mode == 2 && m.part[c] != m.mypart) continue;   // this rank's private children only
         const int* inv = m.cinv + m.cinv_off[k];
         int nbc = m.nb[c];
         int cc = inv[cs];
@@ -438,6 +438,7 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
         int nblk = 0;
         for (int cs = 0; cs < np; ++cs) nblk += ns + 1 - cs;
         for (int blk0 = warp; blk0 < nblk; blk0 += 2 * NW) {
+            if (blk0 == warp) PHASE(40); else if (blk0 == warp + 2 * NW) PHASE(43);
             double v[2][3], tv[2][MAXC][3];
             int i0s[2], j0s[2];
             bool rhss[2], valid[2];
@@ -504,6 +505,7 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
                     }
                 }
             }
+            if (blk0 == warp) PHASE(41);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (!valid[u]) continue;
@@ -518,6 +520,7 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
                         if (lane + 32 * j < 81) P[(i0s[u] + ea[j]) + (j0s[u] + eb[j]) * ld] = v[u][j];
                 }
             }
+            if (blk0 == warp) PHASE(42);
         }
     }
     __syncthreads();

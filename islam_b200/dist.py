@@ -1,0 +1,104 @@
+"""Multi-GPU PVGO: contiguous pose windows, one process per GPU, torch.distributed (NCCL over NVLink) for the exchange.
+
+SURVEY.md section 8e: the top log2(G) levels of the nested-dissection tree are the cuts between windows.  Every rank
+owns the factors that touch its private poses, eliminates its own subtree, and contributes partial panels of the
+shared (separator) fronts; ONE all-reduce per LM try sums those panels (plus the partial linearisation loss), after
+which every rank factors the few shared fronts redundantly and back-substitutes its own window.  A second, 2-double
+all-reduce carries the trial loss / quality term so that all ranks take the same accept / roll-back decision.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import IslamError, LMState
+from .solver import PVGOSolver
+
+
+def _wrap(ptr, n, device):
+    """A float64 tensor view over library-owned device memory (no copy), via the CUDA array interface."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 3}
+    return torch.as_tensor(h, device=device)
+
+
+class ShardedPVGO:
+    """One graph sharded over `world` ranks (world a power of two).  Collectives go through `group`; with the gloo
+    backend (CPU test rigs) the buffers are staged through host memory."""
+
+    def __init__(self, N, links, device, rank=None, world=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        if self.world & (self.world - 1):
+            raise IslamError('the number of windows must be a power of two')
+        self.s = PVGOSolver(N, links, device=device, n_parts=self.world, part=self.rank)
+        L, h = self.s.L, self.s._h
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(L.islam_pvgo_shared_buffer(h, C.byref(p), C.byref(n)), 'islam_pvgo_shared_buffer')
+        self.shared = _wrap(p.value, n.value, self.s.device)
+        _lib.check(L.islam_pvgo_sums_buffer(h, C.byref(p), C.byref(n)), 'islam_pvgo_sums_buffer')
+        self.sums = _wrap(p.value, n.value, self.s.device)
+        parts = np.zeros(N, np.int32)
+        _lib.check(L.islam_pvgo_node_parts(h, parts.ctypes.data), 'islam_pvgo_node_parts')
+        self.node_parts = parts
+        mine = (parts == self.rank) | ((parts < 0) & (self.rank == 0))
+        self._mine = torch.as_tensor(mine, device=self.s.device)
+        self._nccl = dist.get_backend(group) == 'nccl'
+
+    # passthroughs
+    def set_problem(self, *a, **k):
+        self.s.set_problem(*a, **k)
+
+    def set_state(self, nodes, vels):
+        self.s.set_state(nodes, vels)
+
+    def lm_reset(self, **kw):
+        self.s.lm_reset(**kw)
+
+    def _allreduce(self, t):
+        if self._nccl:
+            dist.all_reduce(t, group=self.group)
+        else:                                   # gloo: stage through the host
+            c = t.cpu()
+            dist.all_reduce(c, group=self.group)
+            t.copy_(c)
+
+    def lm_try(self):
+        s = self.s
+        st = C.c_void_p(s.stream.cuda_stream)
+        with torch.cuda.stream(s.stream):
+            _lib.check(s.L.islam_pvgo_lm_try_begin(s._h, st), 'islam_pvgo_lm_try_begin')
+            self._allreduce(self.shared)
+            _lib.check(s.L.islam_pvgo_lm_try_mid(s._h, st), 'islam_pvgo_lm_try_mid')
+            self._allreduce(self.sums)
+            _lib.check(s.L.islam_pvgo_lm_try_end(s._h, st), 'islam_pvgo_lm_try_end')
+
+    def lm_run(self, budget=None):
+        """The `while scheduler.continual()` loop: tries are enqueued back to back (device-side predicates make
+        surplus tries no-ops); one synchronisation at the end, more only if rejected tries exhaust the budget."""
+        s = self.s
+        s._enter()
+        budget = (s.params.max_steps + 2) if budget is None else budget
+        for _ in range(64):
+            for _ in range(budget):
+                self.lm_try()
+            st = s.lm_state()
+            if not st.continual:
+                return st
+            budget = 4
+        return st
+
+    def get_state(self):
+        """Each pose is taken from the rank that solves it (shared poses from rank 0) and summed across ranks."""
+        n, v = self.s.get_state()
+        m = self._mine.unsqueeze(-1)
+        n = torch.where(m, n, torch.zeros_like(n))
+        v = torch.where(m, v, torch.zeros_like(v))
+        self._allreduce(n)
+        self._allreduce(v)
+        return n, v

@@ -111,3 +111,43 @@ def test_window_with_scheduler_matches_oracle():
     n, v = s.align(g.init_nodes[0])
     rn, rv = ref.aligned(g.init_nodes[0])
     assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= 1e-5
+
+
+def _mg_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', device_id=dev)
+    from islam_b200.dist import ShardedPVGO
+    g = synth.config2(N=600, band=8)
+    sh = ShardedPVGO(g.N, g.links, dev)
+    sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
+    sh.set_state(g.init_nodes, g.init_vels)
+    sh.lm_reset(radius=g.radius, max_steps=5, use_scheduler=0)
+    st = sh.lm_run()
+    n, v = sh.get_state()
+    if rank == 0:
+        torch.save(dict(nodes=n.cpu(), vels=v.cpu(), loss=st.loss, steps=st.steps_done), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_lm_matches_single_gpu_and_oracle(world, tmp_path):
+    """contiguous pose windows + one all-reduce of separator panels per try; identical decisions on all ranks."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'mg.pt')
+    mp.spawn(_mg_worker, args=(world, 29533 + world, out), nprocs=world, join=True)
+    r = torch.load(out)
+    g = synth.config2(N=600, band=8)
+    s = _solver(g)
+    s.lm_reset(radius=g.radius, max_steps=5, use_scheduler=0)
+    st = s.lm_run()
+    n1, v1 = s.get_state()
+    assert r['steps'] == 5 and abs(r['loss'] - st.loss) <= 1e-9 * st.loss
+    assert (r['nodes'] - n1.cpu()).abs().max().item() <= 1e-6
+    ref = po.SparseLM(g, np.float64).run(steps=5)
+    assert po.rel_pose_error(r['nodes'].numpy(), ref.nodes)['rel'] <= 1e-5

@@ -27,3 +27,5 @@ for jb in range(8):
     print('jb', jb, 'chol', c[10 + 3 * jb] - t0, 'trsm', c[11 + 3 * jb] - t0, 'update', c[12 + 3 * jb] - t0)
 for k in (3, 4, 5):
     print(names[k], c[k] - t0)
+
+print('A iter0: issue done', c[41]-c[40], 'sum+store done', c[42]-c[40], 'iter1 start', c[43]-c[40])
