@@ -574,40 +574,43 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
         // 3. trailing update of the later block columns: 4-row x 9-column register tiles
         const int ncb = np - 1 - jb;
         if (ncb > 0) {
-            // column block cb only needs rows >= 9 cb (lower trapezoid): its own row-tile count S_cb
+            // column block cb only needs rows >= 9 cb (lower trapezoid).  Tasks are 4-row x 3-column register tiles:
+            // small enough that all 16 warps share the fp64 pipes evenly.
             int tasks = 0;
-            for (int cb = jb + 1; cb < np; ++cb) tasks += (Rf - 9 * cb + 3) >> 2;
+            for (int cb = jb + 1; cb < np; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
             for (int t = tid; t < tasks; t += F3_THREADS) {
-                int cb = jb + 1, rt = t;
-                while (rt >= ((Rf - 9 * cb + 3) >> 2)) { rt -= (Rf - 9 * cb + 3) >> 2; ++cb; }
-                const int j0 = 9 * cb, S = (Rf - j0 + 3) >> 2;
+                int cb = jb + 1, rem = t;
+                while (rem >= 3 * ((Rf - 9 * cb + 3) >> 2)) { rem -= 3 * ((Rf - 9 * cb + 3) >> 2); ++cb; }
+                const int S = (Rf - 9 * cb + 3) >> 2;
+                const int c3 = rem / S, rt = rem - c3 * S;
+                const int j0 = 9 * cb, jc = j0 + 3 * c3;
                 int ix[4];
                 bool vx[4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) { ix[x] = j0 + rt + x * S; vx[x] = ix[x] < Rf; if (!vx[x]) ix[x] = j0; }
-                double acc[4][9];
+                double acc[4][3];
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 9; ++y) acc[x][y] = 0.0;
+                    for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
 #pragma unroll
                 for (int q = 0; q < 9; ++q) {
                     const double* col = P + (c0 + q) * ld;
-                    double av[4];
+                    double av[4], bv[3];
 #pragma unroll
                     for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
 #pragma unroll
-                    for (int y = 0; y < 9; ++y) {
-                        double bv = col[j0 + y];
+                    for (int y = 0; y < 3; ++y) bv[y] = col[jc + y];
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) acc[x][y] += av[x] * bv;
-                    }
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) acc[x][y] += av[x] * bv[y];
                 }
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
                     if (vx[x])
 #pragma unroll
-                        for (int y = 0; y < 9; ++y) P[ix[x] + (j0 + y) * ld] -= acc[x][y];
+                        for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
             }
         }
         __syncthreads();
@@ -622,7 +625,9 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
         Lg[idx] = P[i + j * ld];
     }
 
+#ifdef ISLAM_PHASE_CLOCKS
     __syncthreads();
+#endif
     PHASE(4);
     // D. update matrix on the boundary (+ rhs row): U = pass-through - L21 L21^T.
     // 4x4 register tiles over the lower triangle; operands are LDS.128 pairs (columns of the panel are 32-byte aligned).
@@ -718,7 +723,9 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
                 }
         }
     }
+#ifdef ISLAM_PHASE_CLOCKS
     __syncthreads();
+#endif
     PHASE(5);
 }
 
