@@ -17,7 +17,9 @@
  *     allocated by the caller (PyTorch).  The library owns only its handle and workspace.
  *   - Every call takes the cudaStream_t to enqueue on (as void*), is asynchronous unless stated, and is
  *     CUDA-graph capturable except the functions marked "synchronises".
- *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.
+ *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.  islam_pvgo_create: -2 bad edge list,
+ *     -5 boundary too wide for the back-substitution kernel, -7 loop-closure root above 256 poses (dense-root path
+ *     not implemented yet).
  *   - Numerical failure of the Cholesky (non-positive pivot / NaN) does not abort: it raises `info` in the
  *     LM state, and the step is abandoned exactly as PyPose's "Linear solver failed. Breaking..." path.
  *   - A handle is not thread-safe; use one per host thread / stream.

@@ -227,6 +227,10 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     int rc = build_plan(N, E, links, so, h->plan);
     if (rc != 0) { delete h; return rc; }
     Plan& p = h->plan;
+    // Loop-closure endpoints are eliminated last as one dense root; the dedicated tiled dense-root path (needed for
+    // BASELINE config 4: 2 000 closures => ~4 000 root poses) is not implemented yet, so refuse instead of asking
+    // cudaMalloc for terabytes of update matrices.
+    if (p.root_pivots > 256 || p.U_doubles + p.L_doubles > (1LL << 34)) { delete h; return -7; }
     islam_lm_default_params(&h->prm);
 
 #define UP(buf, vec) do { cudaError_t _e = h->buf.upload(vec); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
