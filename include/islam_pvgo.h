@@ -184,6 +184,10 @@ int islam_plan_build(islam_plan** out, int32_t N, int32_t E, const int64_t* link
 void islam_plan_free(islam_plan* p);
 int64_t islam_plan_array(const islam_plan* p, const char* name, const void** ptr); /* returns length or -1 */
 
+/* ordered prefix product over n elements (pp.cumprod; Datasets/transformation.py:100-113 motion2pose_pypose is
+ * left = 0 with the start pose prepended): left = 1: y_i = x_i * y_{i-1};  left = 0: y_i = y_{i-1} * x_i */
+int islam_lie_cumprod(int32_t group, const float* x, float* y, int64_t n, int32_t left, void* stream);
+
 const char* islam_version(void);
 
 #ifdef __cplusplus

@@ -87,6 +87,7 @@ _SIGS = {
     'islam_lie_inv_bwd': (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P]),
     'islam_lie_mul_bwd': (C.c_int, [C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
     'islam_lie_act_bwd': (C.c_int, [C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    'islam_lie_cumprod': (C.c_int, [C.c_int32, _P, _P, C.c_int64, C.c_int32, _P]),
     'islam_plan_build': (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P, C.POINTER(PvgoOpts)]),
     'islam_plan_free': (None, [_P]),
     'islam_plan_array': (C.c_int64, [_P, C.c_char_p, C.POINTER(_P)]),

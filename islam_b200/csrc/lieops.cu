@@ -176,6 +176,60 @@ __global__ void k_act_bwd(int group, const float* x, const float* p_, const floa
     }
 }
 
+// ordered prefix product along the leading dimension (pp.cumprod): left = 1: y_i = x_i * y_{i-1}; left = 0: y_i = y_{i-1} * x_i.
+// One block; float64 accumulation (a 5 000-element float32 chain would drift by ~1e-5).  Datasets/transformation.py:100-113
+// (motion2pose_pypose) is this scan with left = 0.
+constexpr int CP_THREADS = 512;
+template <int GROUP>
+__global__ void __launch_bounds__(CP_THREADS) k_cumprod(const float* __restrict__ x, float* __restrict__ y, int64_t n, int left) {
+    constexpr int W = GROUP == ISLAM_SE3 ? 7 : 4;
+    __shared__ double sq[CP_THREADS][W];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + CP_THREADS - 1) / CP_THREADS;
+    const int64_t b = min(n, (int64_t)t * chunk), e = min(n, b + chunk);
+    auto mul = [&](const double* A, const double* B, double* O) {      // O = left ? B*A : A*B  (A earlier, B later)
+        if (GROUP == ISLAM_SE3) { if (left) se3_mul(B, A, O); else se3_mul(A, B, O); }
+        else { if (left) q_mul(B, A, O); else q_mul(A, B, O); }
+    };
+    double acc[W], cur[W], tmp[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = (k == W - 1) ? 1.0 : 0.0;
+    for (int64_t i = b; i < e; ++i) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) cur[k] = (double)x[W * i + k];
+        mul(acc, cur, tmp);
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] = tmp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) sq[t][k] = acc[k];
+    __syncthreads();
+    for (int d = 1; d < CP_THREADS; d <<= 1) {
+        double a[W], r[W];
+        const bool act = t >= d;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { a[k] = sq[t - d][k]; r[k] = sq[t][k]; }
+            mul(a, r, tmp);
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) sq[t][k] = tmp[k];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = (t > 0) ? sq[t - 1][k] : ((k == W - 1) ? 1.0 : 0.0);
+    for (int64_t i = b; i < e; ++i) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) cur[k] = (double)x[W * i + k];
+        mul(acc, cur, tmp);
+#pragma unroll
+        for (int k = 0; k < W; ++k) { acc[k] = tmp[k]; y[W * i + k] = (float)tmp[k]; }
+    }
+}
+
 inline int chk(int group, int64_t n) { return (group != ISLAM_SE3 && group != ISLAM_SO3) || n < 0 ? -1 : 0; }
 inline unsigned grid(int64_t n) { return (unsigned)((n + T - 1) / T); }
 
@@ -197,3 +251,11 @@ extern "C" int islam_lie_log_bwd(int32_t group, const float* y, const float* gy,
 extern "C" int islam_lie_inv_bwd(int32_t group, const float* y, const float* gy, float* gx, int64_t n, void* stream) { LAUNCH(k_inv_bwd, y, gy, gx); }
 extern "C" int islam_lie_mul_bwd(int32_t group, const float* a, const float* gy, float* ga, float* gb, int64_t n, void* stream) { LAUNCH(k_mul_bwd, a, gy, ga, gb); }
 extern "C" int islam_lie_act_bwd(int32_t group, const float* x, const float* p, const float* gy, float* gx, float* gp, int64_t n, void* stream) { LAUNCH(k_act_bwd, x, p, gy, gx, gp); }
+
+extern "C" int islam_lie_cumprod(int32_t group, const float* x, float* y, int64_t n, int32_t left, void* stream) {
+    if (chk(group, n) || !x || !y) return -1;
+    if (n == 0) return 0;
+    if (group == ISLAM_SE3) k_cumprod<ISLAM_SE3><<<1, CP_THREADS, 0, (cudaStream_t)stream>>>(x, y, n, left);
+    else k_cumprod<ISLAM_SO3><<<1, CP_THREADS, 0, (cudaStream_t)stream>>>(x, y, n, left);
+    return (int)cudaGetLastError();
+}

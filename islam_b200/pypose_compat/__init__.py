@@ -284,12 +284,11 @@ def Inv(x):
     return x.Inv()
 
 
-def cumprod(x, dim=0):
-    """pp.cumprod along the (only supported) leading dimension — used by callers that chain relative motions."""
-    out = [x[0]]
-    for i in range(1, x.shape[0]):
-        out.append(out[-1] @ x[i])
-    return LieTensor(torch.stack([o.tensor() for o in out]), ltype=x.ltype)
+def cumprod(x, dim=0, left=True):
+    """pp.cumprod along the leading dimension (prefix-product scan kernel, csrc/lieops.cu)."""
+    if dim not in (0, -2) or x.dim() != 2:
+        raise IslamError('cumprod is implemented along the leading dimension of a (n, W) LieTensor')
+    return LieTensor(_ops.cumprod(x.tensor(), x.ltype.group, left), ltype=x.ltype)
 
 
 from . import module, optim, function          # noqa: E402

@@ -146,3 +146,18 @@ class ActFn(torch.autograd.Function):
         g = _prep(gy.expand(pd.shape), xd.device, 3)
         gx, gp = _call('islam_lie_act_bwd', ctx.group, [xd, pd, g], [xd.shape, pd.shape], xd.device)
         return _back(gx, gy).sum_to_size(ctx.sx), _back(gp, gy).sum_to_size(ctx.sp), None
+
+
+def cumprod(x, group, left=True):
+    """Ordered prefix product along dim 0 of a (n, W) tensor; no autograd (the reference only uses it detached)."""
+    dev = _dev(x)
+    xd = _prep(x, dev, _EMB[group])
+    if xd.dim() != 2:
+        raise IslamError('cumprod expects a (n, W) LieTensor')
+    y = torch.empty_like(xd)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.islam_lie_cumprod(group, C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), xd.shape[0],
+                                       1 if left else 0, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   'islam_lie_cumprod')
+    return _back(y, x)

@@ -108,3 +108,33 @@ def test_add__is_left_retraction():
     x.add_(torch.tensor(d, device=DEV))
     ref = lie.se3_retract(X.astype(np.float64), d.astype(np.float64))
     assert np.abs(x.tensor().cpu().numpy() - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize('dev', ['cuda:0', 'cpu'])
+def test_trajectory_chaining_helpers(dev):
+    """Datasets/transformation.py:100-124 semantics (train.py:220,225,240,264) on the scan / batched kernels."""
+    from islam_b200.transformation import motion2pose_pypose, pose2motion_pypose, tartan2kitti_pypose, cvtSE3_pypose
+    n = 3000
+    M = (lie.se3_exp(np.random.default_rng(20).standard_normal((n, 6)) * np.array([.3, .3, .3, .05, .05, .05]))).astype(np.float32)
+    T0 = _rand_se3(1, 21)[0]
+    poses = motion2pose_pypose(pp.SE3(torch.tensor(M, device=dev)), pp.SE3(torch.tensor(T0, device=dev)))
+    assert poses.shape == (n + 1, 7) and poses.ltype is pp.SE3_type
+    ref = [T0.astype(np.float64)]
+    for m in M.astype(np.float64):
+        ref.append(lie.se3_mul(ref[-1], m))
+    ref = np.stack(ref)
+    got = poses.tensor().cpu().numpy().astype(np.float64)
+    assert np.abs(got[:, :3] - ref[:, :3]).max() < 1e-4 * max(1.0, np.abs(ref[:, :3]).max())
+    assert np.abs(lie.quat_canon(got[:, 3:]) - lie.quat_canon(ref[:, 3:])).max() < 1e-5
+    back = pose2motion_pypose(poses)
+    assert back.shape == (n, 7)
+    d = lie.se3_log(lie.se3_mul(lie.se3_inv(M.astype(np.float64)), back.tensor().cpu().numpy().astype(np.float64)))
+    assert np.abs(d).max() < 2e-3                                      # float32 poses ~100 m away
+    k = tartan2kitti_pypose(torch.tensor(lie.se3_log(M[:5].astype(np.float64)), dtype=torch.float32, device=dev))
+    assert k.shape == (5, 7)
+    left = pp.cumprod(pp.SE3(torch.tensor(M[:50], device=dev)), left=True).tensor().cpu().numpy()
+    r = M[0].astype(np.float64)
+    for m in M[1:50].astype(np.float64):
+        r = lie.se3_mul(m, r)
+    assert np.abs(left[-1] - r).max() < 1e-4
+    assert cvtSE3_pypose(pp.SE3(torch.tensor(M[:2], device=dev))).ltype is pp.SE3_type
