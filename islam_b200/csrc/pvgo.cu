@@ -329,7 +329,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
         int nch = p.f_child_off[f + 1] - p.f_child_off[f];
         long long meta = front_meta_doubles(p.f_np[f], p.f_np[f] + p.f_nb[f], nch);
-        long long need = ((Rf + 3) & ~3LL) * Cf + 96 + meta;
+        long long need = ((Rf + 3) & ~3LL) * Cf + 192 + meta;
         if (need > h->max_smem_doubles || meta == 0) h->level_fast[l] = 0;   // this level takes the generic kernel
         if (need > h->max_smem_doubles) need = 96 + meta;        // panel stays in global memory
         if (need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;

@@ -416,13 +416,13 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
     constexpr int NW = F3_THREADS / 32;
     PHASE(0);
     extern __shared__ double smem[];
-    double* sLinv = smem;                      // 81 (+ pad to 96)
+    double* sLinv = smem;                      // 2 x 81 (+ pad): double-buffered inverse diagonal blocks
     FrontCtx c;
-    stage_front(m, f, (int*)(smem + 96), c);
+    stage_front(m, f, (int*)(smem + 192), c);
     const int np = c.np, nb = c.nb, ns = c.ns;
     const int Cf = 9 * np, Rb = 9 * nb, Rf = Cf + Rb + 1, ub = Rb + 1;
     const int ld = (Rf + 3) & ~3;              // 32-byte aligned columns: LDS.128 on row quads
-    double* P = smem + 96 + front_meta_doubles(np, ns, c.nch);
+    double* P = smem + 192 + front_meta_doubles(np, ns, c.nch);
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
     const double* base = (stage == 2) ? shared + m.shared_off[f] : nullptr;
@@ -526,34 +526,39 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
     __syncthreads();
     PHASE(2);
 
-    // B. right-looking blocked Cholesky of the panel
+    // B. right-looking blocked Cholesky of the panel with look-ahead: while warps 1..15 apply block column jb to the
+    // trailing columns, warp 0 updates just the next 9x9 diagonal block, factors and inverts it (the serial part), so
+    // the single-warp latency hides behind the bulk update.  sLinv is double-buffered.
     bool ok = true;
-    for (int jb = 0; jb < np; ++jb) {
-        const int c0 = 9 * jb;
-        if (warp == 0) {                                     // 1. diagonal block: factor + invert (registers)
-            double A[45], linv[9];
+    auto diag_block = [&](int jbn, double* Lout) {           // warp 0 only: P diag block (already updated) -> L, Linv
+        const int d0 = 9 * jbn;
+        double A[45], linv[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int q = 0; q <= r; ++q) A[r * (r + 1) / 2 + q] = P[(d0 + r) + (d0 + q) * ld];
+        ok = chol9_rl(A, linv) && ok;
+        __syncwarp();
+        if (lane == 0) {
 #pragma unroll
             for (int r = 0; r < 9; ++r)
 #pragma unroll
-                for (int q = 0; q <= r; ++q) A[r * (r + 1) / 2 + q] = P[(c0 + r) + (c0 + q) * ld];
-            ok = chol9_rl(A, linv) && ok;
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int r = 0; r < 9; ++r)
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) P[(c0 + r) + (c0 + q) * ld] = (q <= r) ? A[r * (r + 1) / 2 + (q <= r ? q : 0)] : 0.0;
-            }
-            if (lane < 9) {
-                double x[9];
-                tri_inv_col_uniform(A, linv, lane, x);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) sLinv[9 * i + lane] = x[i];
-            }
+                for (int q = 0; q < 9; ++q) P[(d0 + r) + (d0 + q) * ld] = (q <= r) ? A[r * (r + 1) / 2 + (q <= r ? q : 0)] : 0.0;
         }
-        __syncthreads();
+        if (lane < 9) {
+            double x[9];
+            tri_inv_col_uniform(A, linv, lane, x);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Lout[9 * i + lane] = x[i];
+        }
+    };
+    if (warp == 0) diag_block(0, sLinv);
+    __syncthreads();
+    for (int jb = 0; jb < np; ++jb) {
+        const int c0 = 9 * jb;
+        const double* sLi = sLinv + 96 * (jb & 1);
         PHASE(10 + 3 * jb);
-        if (tid < 81) Linv[81 * (size_t)c.nodes[jb] + tid] = sLinv[tid];
+        if (tid < 81) Linv[81 * (size_t)c.nodes[jb] + tid] = sLi[tid];
         // 2. rows below the diagonal block: x = Lkk^-1 applied from the right
         for (int i = c0 + 9 + tid; i < Rf; i += F3_THREADS) {
             double acc[9], x[9];
@@ -563,7 +568,7 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
             for (int q = 0; q < 9; ++q) {
                 double s_ = 0.0;
 #pragma unroll
-                for (int k = 0; k <= q; ++k) s_ += acc[k] * sLinv[9 * q + k];
+                for (int k = 0; k <= q; ++k) s_ += acc[k] * sLi[9 * q + k];
                 x[q] = s_;
             }
 #pragma unroll
@@ -571,46 +576,64 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
         }
         __syncthreads();
         PHASE(11 + 3 * jb);
-        // 3. trailing update of the later block columns: 4-row x 9-column register tiles
+        // 3. trailing update; warp 0 takes the next diagonal block (update + Cholesky + inverse), warps 1.. the rest
         const int ncb = np - 1 - jb;
         if (ncb > 0) {
-            // column block cb only needs rows >= 9 cb (lower trapezoid).  Tasks are 4-row x 3-column register tiles:
-            // small enough that all 16 warps share the fp64 pipes evenly.
-            int tasks = 0;
-            for (int cb = jb + 1; cb < np; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
-            for (int t = tid; t < tasks; t += F3_THREADS) {
-                int cb = jb + 1, rem = t;
-                while (rem >= 3 * ((Rf - 9 * cb + 3) >> 2)) { rem -= 3 * ((Rf - 9 * cb + 3) >> 2); ++cb; }
-                const int S = (Rf - 9 * cb + 3) >> 2;
-                const int c3 = rem / S, rt = rem - c3 * S;
-                const int j0 = 9 * cb, jc = j0 + 3 * c3;
-                int ix[4];
-                bool vx[4];
+            if (warp == 0) {
+                const int d0 = c0 + 9;
+                for (int e = lane; e < 45; e += 32) {            // lower triangle of the next diagonal block
+                    int r = 0;
+                    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+                    const int q = e - r * (r + 1) / 2;
+                    double s_ = 0.0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x) { ix[x] = j0 + rt + x * S; vx[x] = ix[x] < Rf; if (!vx[x]) ix[x] = j0; }
-                double acc[4][3];
+                    for (int k = 0; k < 9; ++k) s_ += P[(d0 + r) + (c0 + k) * ld] * P[(d0 + q) + (c0 + k) * ld];
+                    P[(d0 + r) + (d0 + q) * ld] -= s_;
+                }
+                __syncwarp();
+                diag_block(jb + 1, sLinv + 96 * ((jb + 1) & 1));
+            } else {
+                // column block cb only needs rows >= 9 cb (lower trapezoid); the 9 diagonal rows of block jb+1 are warp 0's
+                int tasks = 0;
+                for (int cb = jb + 1; cb < np; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
+                for (int t = tid - 32; t < tasks; t += F3_THREADS - 32) {
+                    int cb = jb + 1, rem = t;
+                    while (rem >= 3 * ((Rf - 9 * cb + 3) >> 2)) { rem -= 3 * ((Rf - 9 * cb + 3) >> 2); ++cb; }
+                    const int S = (Rf - 9 * cb + 3) >> 2;
+                    const int c3 = rem / S, rt = rem - c3 * S;
+                    const int j0 = 9 * cb, jc = j0 + 3 * c3;
+                    int ix[4];
+                    bool vx[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    const double* col = P + (c0 + q) * ld;
-                    double av[4], bv[3];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) bv[y] = col[jc + y];
+                    for (int x = 0; x < 4; ++x) {
+                        ix[x] = j0 + rt + x * S;
+                        vx[x] = ix[x] < Rf && !(cb == jb + 1 && ix[x] < j0 + 9);
+                        if (!vx[x]) ix[x] = j0;
+                    }
+                    double acc[4][3];
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
-                        for (int y = 0; y < 3; ++y) acc[x][y] += av[x] * bv[y];
+                        for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const double* col = P + (c0 + q) * ld;
+                        double av[4], bv[3];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) bv[y] = col[jc + y];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 3; ++y) acc[x][y] += av[x] * bv[y];
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+                        if (vx[x])
+#pragma unroll
+                            for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
                 }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (vx[x])
-#pragma unroll
-                        for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
             }
         }
         __syncthreads();

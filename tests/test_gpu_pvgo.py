@@ -197,3 +197,40 @@ def test_config4_style_loop_closures_and_size_guard():
     from islam_b200._lib import IslamError
     with pytest.raises(IslamError):
         PVGOSolver(big.N, big.links)
+
+
+def test_rejected_tries_follow_the_oracle():
+    """A badly perturbed initial guess makes Gauss-Newton overshoot: the second step burns 4 rejected tries before it is
+    accepted.  The device-side roll-back, cumulative damping (A.diag += A.diag * damping per retry) and reject counting must
+    follow SURVEY.md A.4 step by step."""
+    from oracle import lie
+    g = synth.config2(N=60, band=2)
+    d = np.random.default_rng(1).standard_normal((g.N, 6)) * np.array([2, 2, 2, 0.8, 0.8, 0.8])
+    g.init_nodes = lie.se3_retract(g.init_nodes.astype(np.float64), d).astype(np.float32)
+    ref = po.SparseLM(g, np.float64, radius=1e6)
+    s = _solver(g)
+    s.lm_reset(radius=1e6, max_steps=5, use_scheduler=0)
+    rejects = []
+    for k in range(5):
+        ref.step()
+        st = s.lm_step()
+        h = ref.history[-1]
+        rejects.append(h['rejects'])
+        assert st.reject_count == h['rejects'], (k, st.as_dict(), h)
+        assert abs(st.loss - h['loss']) <= 1e-3 * max(1.0, abs(h['loss'])), (k, st.loss, h['loss'])
+        assert abs(st.damping - h['damping']) <= 1e-9 * h['damping'], (k, st.damping, h['damping'])
+    assert max(rejects) >= 2, rejects
+    assert st.tries_total == 5 + sum(rejects)
+    n, _ = s.align(g.init_nodes[0])
+    rn, _ = ref.aligned(g.init_nodes[0])
+    assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= 1e-4      # far from convergence, rotations ~1 rad: float32 state
+
+
+def test_run_with_scheduler_stops_like_stop_on_plateau():
+    g = synth.config2(N=200, band=4)
+    ref = po.SparseLM(g, np.float64).run()                      # StopOnPlateau(10, 3, 1e-3)
+    s = _solver(g)
+    s.lm_reset(radius=g.radius, max_steps=10, patience=3, decreasing=1e-3, use_scheduler=1)
+    st = s.lm_run()
+    assert st.steps_done == len(ref.history) and st.continual == 0
+    assert abs(st.loss - ref.history[-1]['loss']) <= 1e-4 * abs(ref.history[-1]['loss'])
