@@ -25,7 +25,7 @@ struct ProblemView {
     const int* edge_owner;  // [E] window that owns the factor (multi-GPU) or nullptr
     const int* pair_owner;  // [M]
     int part;
-    double w0, w1, w2, w3;  // information scalars (pvgo.py:125-129)
+    const double* w;        // [4] information scalars w0..w3 in device memory (pvgo.py:125-129)
 };
 
 struct LinBuffers {
@@ -131,13 +131,13 @@ k_vo(const LMState* __restrict__ st, const float* __restrict__ nodes0, const flo
                 double qa = 0.0;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) qa += J6[k][a] * (double)r[k];
-                qo[a] = pv.w0 * qa;
+                qo[a] = pv.w[0] * qa;
 #pragma unroll
                 for (int b = 0; b < 6; ++b) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) s += J6[k][a] * J6[k][b];
-                    So[6 * a + b] = pv.w0 * s;
+                    So[6 * a + b] = pv.w[0] * s;
                 }
             }
 #pragma unroll
@@ -286,20 +286,20 @@ k_assemble_nodes(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, 
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += (double)Jp[3 * k + aa] * (double)Jp[3 * k + bb];
-                v += pv.w2 * s;
+                v += pv.w[2] * s;
             }
             if (has_next) {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += (double)Jn[3 * k + aa] * (double)Jn[3 * k + bb];
-                v += pv.w2 * s;
+                v += pv.w[2] * s;
             }
         }
         if (a == b) {
-            if (a < 3) v += (has_prev ? pv.w3 : 0.0) + (has_next ? pv.w3 : 0.0);               // transvel tau
-            if (a >= 6) v += (has_prev ? pv.w1 : 0.0) + (has_next ? pv.w1 + pv.w3 * dtn * dtn : 0.0);
+            if (a < 3) v += (has_prev ? pv.w[3] : 0.0) + (has_next ? pv.w[3] : 0.0);               // transvel tau
+            if (a >= 6) v += (has_prev ? pv.w[1] : 0.0) + (has_next ? pv.w[1] + pv.w[3] * dtn * dtn : 0.0);
         }
-        if (has_next && ((a < 3 && b == a + 6) || (b < 3 && a == b + 6))) v += pv.w3 * dtn;   // tau_i - v_i cross
+        if (has_next && ((a < 3 && b == a + 6) || (b < 3 && a == b + 6))) v += pv.w[3] * dtn;   // tau_i - v_i cross
         Hd[81 * (size_t)n + idx] = v;
     }
     if (lane < 9) {
@@ -316,26 +316,26 @@ k_assemble_nodes(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, 
         const float* rp = lb.r_imu + 9 * (size_t)(n - 1);
         const float* rn = lb.r_imu + 9 * (size_t)n;
         if (a < 3) {
-            if (has_prev) v += pv.w3 * (double)rp[6 + a];
-            if (has_next) v -= pv.w3 * (double)rn[6 + a];
+            if (has_prev) v += pv.w[3] * (double)rp[6 + a];
+            if (has_next) v -= pv.w[3] * (double)rn[6 + a];
         } else if (a < 6) {
             int aa = a - 3;
             if (has_prev) {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += (double)Jp[3 * k + aa] * (double)rp[3 + k];
-                v += pv.w2 * s;
+                v += pv.w[2] * s;
             }
             if (has_next) {
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += (double)Jn[3 * k + aa] * (double)rn[3 + k];
-                v -= pv.w2 * s;
+                v -= pv.w[2] * s;
             }
         } else {
             int aa = a - 6;
-            if (has_prev) v -= pv.w1 * (double)rp[aa];
-            if (has_next) v += pv.w1 * (double)rn[aa] - pv.w3 * dtn * (double)rn[6 + aa];
+            if (has_prev) v -= pv.w[1] * (double)rp[aa];
+            if (has_next) v += pv.w[1] * (double)rn[aa] - pv.w[3] * dtn * (double)rn[6 + aa];
         }
         g[9 * (size_t)n + a] = v;
     }
@@ -369,13 +369,13 @@ k_assemble_pairs(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, 
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) s += (double)Jr[3 * k + a - 3] * (double)Jr[3 * k + b - 3];
-                v -= pv.w2 * s;
+                v -= pv.w[2] * s;
             }
             if (a == b) {
-                if (a < 3) v -= pv.w3;
-                if (a >= 6) v -= pv.w1;
+                if (a < 3) v -= pv.w[3];
+                if (a >= 6) v -= pv.w[1];
             }
-            if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w3 * dt;   // (v_lo, tau_hi)
+            if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w[3] * dt;   // (v_lo, tau_hi)
         }
         Ho[81 * (size_t)p + idx] = v;
     }

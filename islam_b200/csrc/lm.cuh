@@ -82,8 +82,9 @@ __device__ __forceinline__ void lm_end_step(LMState* st, const islam_lm_params& 
 }
 
 // trial loss + trust-region update + accept / roll back
-__global__ void k_lm_control(LMState* st, islam_lm_params p, const double* __restrict__ sums) {
+__global__ void k_lm_control(LMState* st, const islam_lm_params* __restrict__ pp, const double* __restrict__ sums) {
     if (threadIdx.x != 0 || !st->active) return;
+    const islam_lm_params p = *pp;
     const double s = sums[0], q = sums[1];
     st->loss_trial = s;
     if (st->chol_fail) {            // "Linear solver failed. Breaking optimization step..." : params untouched
@@ -120,5 +121,29 @@ __global__ void k_lm_control(LMState* st, islam_lm_params p, const double* __res
     }
 }
 
-// ---- outer losses (pvgo.py:67-78, 95-111) and gauge alignment (pvgo.py:114-119) -----------------------------
+// lm_reset without a host round trip: the parameters travel as a kernel argument into device memory, the state is
+// re-initialised in place (the current/trial buffer index survives)
+__global__ void k_lm_reset(LMState* st, islam_lm_params* dst, islam_lm_params p) {
+    if (threadIdx.x != 0) return;
+    *dst = p;
+    const int cur = st->cur;
+    LMState z;
+    memset(&z, 0, sizeof(z));
+    z.cur = cur;
+    z.damping = 1.0 / p.radius; z.radius = p.radius; z.down = p.down; z.diag_scale = 1.0;
+    z.need_linearize = 1; z.continual = 1;
+    *st = z;
+}
+
+// copy of the CURRENT state buffer (selected on the device, so no host synchronisation is needed)
+__global__ void __launch_bounds__(128)
+k_copy_state(const LMState* __restrict__ st, const float* __restrict__ n0, const float* __restrict__ n1,
+             const float* __restrict__ v0, const float* __restrict__ v1, int N, float* __restrict__ nout, float* __restrict__ vout) {
+    const float* ns = st->cur ? n1 : n0;
+    const float* vs = st->cur ? v1 : v0;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nout && i < 7 * N) nout[i] = ns[i];
+    if (vout && i < 3 * N) vout[i] = vs[i];
+}
+
 }  // namespace islam

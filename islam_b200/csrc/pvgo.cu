@@ -168,6 +168,8 @@ struct islam_pvgo {
     DevBuf<long long> d_Loff, d_Uoff, d_shared_off;
     DevBuf<double> Lbuf, Ubuf, Linv, shared;
     DevBuf<LMState> st;
+    DevBuf<islam_lm_params> d_prm;
+    DevBuf<double> d_w;
     LMState* st_host = nullptr;     // pinned mirror
     int nblk_vo = 0, nblk_imu = 0;
     int max_smem_doubles = 0;
@@ -194,7 +196,7 @@ struct islam_pvgo {
         DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared};
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_shared_off.release();
-        st.release();
+        st.release(); d_prm.release(); d_w.release();
     }
 };
 
@@ -307,7 +309,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
     }
     AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles); AL(Linv, 81 * (size_t)N);
-    AL(st, 1);
+    AL(st, 1); AL(d_prm, 1); AL(d_w, 4);
     cudaMemset(h->D.p, 0, sizeof(double) * 9 * (size_t)N);
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
@@ -344,7 +346,9 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     pv.ei = h->ei.p; pv.ej = h->ej.p; pv.Z = h->Z.p; pv.drot = h->drot.p; pv.dtrans = h->dtrans.p;
     pv.dvel = h->dvel.p; pv.dt = h->dt.p;
     pv.edge_owner = h->edge_owner.p; pv.pair_owner = h->pair_owner.p; pv.part = opts.part;
-    pv.w0 = pv.w1 = pv.w2 = pv.w3 = 1.0;
+    pv.w = h->d_w.p;
+    { double ones[4] = {1, 1, 1, 1}; cudaMemcpy(h->d_w.p, ones, sizeof(ones), cudaMemcpyHostToDevice); }
+    cudaMemcpy(h->d_prm.p, &h->prm, sizeof(h->prm), cudaMemcpyHostToDevice);
     LinBuffers& lb = h->lb;
     lb.r_vo = h->r_vo.p; lb.J_vo = h->J_vo.p; lb.S_vo = h->S_vo.p; lb.q_vo = h->q_vo.p; lb.r_imu = h->r_imu.p;
     lb.J_rot = h->J_rot.p; lb.loss_part = h->lin_part.p;
@@ -392,8 +396,7 @@ extern "C" int islam_pvgo_set_problem(islam_pvgo* h, const float* Z, const float
     CK(cudaMemcpyAsync(h->dtrans.p, dtrans, sizeof(float) * 3 * p.M, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->dvel.p, dvel, sizeof(float) * 3 * p.M, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(h->dt.p, dt, sizeof(float) * p.M, cudaMemcpyDeviceToDevice, s));
-    h->pv.w0 = w[0]; h->pv.w1 = w[1]; h->pv.w2 = w[2]; h->pv.w3 = w[3];
-    if (h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }   // weights are kernel arguments
+    CK(cudaMemcpyAsync(h->d_w.p, w, sizeof(double) * 4, cudaMemcpyHostToDevice, s));   // pageable source: staged before return
     return 0;
 }
 
@@ -414,13 +417,10 @@ static int read_state(islam_pvgo* h, cudaStream_t s) {
 
 extern "C" int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, void* stream) {
     if (!h) return -1;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = read_state(h, s);
-    if (rc) return rc;
-    int cur = h->st_host->cur;
-    if (nodes) CK(cudaMemcpyAsync(nodes, h->nodes[cur].p, sizeof(float) * 7 * h->plan.N, cudaMemcpyDeviceToDevice, s));
-    if (vels) CK(cudaMemcpyAsync(vels, h->vels[cur].p, sizeof(float) * 3 * h->plan.N, cudaMemcpyDeviceToDevice, s));
-    return 0;
+    const int N = h->plan.N;
+    k_copy_state<<<(7 * N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
+                                                                         h->vels[1].p, N, nodes, vels);
+    return (int)cudaGetLastError();
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------------------------
@@ -447,11 +447,11 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int
             if (h->level_fast[l])
                 k_factor_fast<<<nloc, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
                                                             h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min,
-                                                            q.lm_max, forced_scale, 0, &h->st.p->chol_fail);
+                                                            q.lm_max, forced_scale, 0, &h->st.p->chol_fail, h->d_prm.p);
             else
                 k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
                                                               h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
-                                                              forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail);
+                                                              forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail, h->d_prm.p);
         }
     }
     return (int)cudaGetLastError();
@@ -478,11 +478,11 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
         if (h->level_fast[l])
             k_factor_fast<<<ns, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
                                                       h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
-                                                      forced_scale, 2, &h->st.p->chol_fail);
+                                                      forced_scale, 2, &h->st.p->chol_fail, h->d_prm.p);
         else
             k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
                                                         h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
-                                                        h->level_smem_doubles[l], 2, &h->st.p->chol_fail);
+                                                        h->level_smem_doubles[l], 2, &h->st.p->chol_fail, h->d_prm.p);
     }
     return (int)cudaGetLastError();
 }
@@ -554,20 +554,10 @@ extern "C" int islam_pvgo_solve(islam_pvgo* h, double diag_scale, double lm_min,
 // ---- LM driver ------------------------------------------------------------------------------------------------------
 extern "C" int islam_pvgo_lm_reset(islam_pvgo* h, const islam_lm_params* p, void* stream) {
     if (!h) return -1;
-    cudaStream_t s = (cudaStream_t)stream;
     if (p) h->prm = *p;
-    if (h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }
-    int rc = read_state(h, s);
-    if (rc) return rc;
-    LMState st;
-    std::memset(&st, 0, sizeof(st));
-    st.cur = h->st_host->cur;
-    st.damping = 1.0 / h->prm.radius; st.radius = h->prm.radius; st.down = h->prm.down; st.diag_scale = 1.0;
-    st.need_linearize = 1; st.continual = 1;
-    *h->st_host = st;
-    CK(cudaMemcpyAsync(h->st.p, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
-    return 0;
+    if (!(h->prm.radius > 0.0)) return -1;
+    k_lm_reset<<<1, 32, 0, (cudaStream_t)stream>>>(h->st.p, h->d_prm.p, h->prm);      // asynchronous; the CUDA graph survives
+    return (int)cudaGetLastError();
 }
 
 static double* lin_sum_ptr(islam_pvgo* h) {          // single GPU: private scratch; multi-GPU: tail of the all-reduce buffer
@@ -615,7 +605,7 @@ static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
 }
 
 static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
-    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->prm, trial_sum_ptr(h));
+    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
     return (int)cudaGetLastError();
 }
 
@@ -648,7 +638,7 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
     k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
                                                   h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
     k_reduce2<<<1, 256, 0, s>>>(h->st.p, part, np_, trial_sum_ptr(h), 0);
-    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->prm, trial_sum_ptr(h));
+    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
     CK(cudaEventRecord(ev[4], s));
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);

@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(FAC_THREADS, 1)
 k_factor_level(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
                const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
                double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
-               const double* __restrict__ shared, double lm_min, double lm_max, double forced_scale, int smem_doubles,
-               int stage, int* chol_fail) {
+               const double* __restrict__ shared, double lm_min_, double lm_max_, double forced_scale, int smem_doubles,
+               int stage, int* chol_fail, const islam_lm_params* __restrict__ prm) {
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x;
     extern __shared__ double smem[];
@@ -407,10 +408,11 @@ __global__ void __launch_bounds__(F3_THREADS, 1)
 k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
               const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
               double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
-              const double* __restrict__ shared, double lm_min, double lm_max, double forced_scale, int stage,
-              int* chol_fail) {
+              const double* __restrict__ shared, double lm_min_, double lm_max_, double forced_scale, int stage,
+              int* chol_fail, const islam_lm_params* __restrict__ prm) {
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = F3_THREADS / 32;

@@ -85,14 +85,16 @@ class PVGOSolver:
         self._enter()
         _lib.check(self.L.islam_pvgo_set_problem(self._h, _ptr(Z), _ptr(dr), _ptr(dp), _ptr(dv), _ptr(dt), C.byref(w),
                                                  self._s()), 'islam_pvgo_set_problem')
-        self.stream.synchronize()                     # inputs may be temporaries
+        for t in (Z, dr, dp, dv, dt):                 # the D2D copies are in flight on our stream: keep the sources alive
+            t.record_stream(self.stream)
 
     def set_state(self, nodes, vels):
         n = _f32(nodes, self.device, (self.N, 7))
         v = _f32(vels, self.device, (self.N, 3))
         self._enter()
         _lib.check(self.L.islam_pvgo_set_state(self._h, _ptr(n), _ptr(v), self._s()), 'islam_pvgo_set_state')
-        self.stream.synchronize()
+        n.record_stream(self.stream)
+        v.record_stream(self.stream)
 
     def get_state(self):
         n, v = self._new(self.N, 7), self._new(self.N, 3)

@@ -234,3 +234,38 @@ def test_run_with_scheduler_stops_like_stop_on_plateau():
     st = s.lm_run()
     assert st.steps_done == len(ref.history) and st.continual == 0
     assert abs(st.loss - ref.history[-1]['loss']) <= 1e-4 * abs(ref.history[-1]['loss'])
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (5 000 poses / 49 962 factors) through size-independent properties: parity with the
+    oracle after the full 10 iterations, bitwise run-to-run determinism, and translation equivariance (every factor of
+    pvgo.py:36-51 only sees position differences, so shifting all initial positions shifts the solution and nothing else)."""
+    g = synth.config2()
+    s = _solver(g)
+
+    def run(nodes):
+        s.set_state(nodes, g.init_vels)
+        s.lm_reset(radius=g.radius, max_steps=10, use_scheduler=0)
+        st = s.lm_run()
+        n, v = s.get_state()
+        return st, n.cpu().numpy().astype(np.float64), v.cpu().numpy().astype(np.float64)
+
+    st1, n1, v1 = run(g.init_nodes)
+    st2, n2, v2 = run(g.init_nodes)
+    assert st1.steps_done == 10 and st1.tries_total == st2.tries_total
+    assert np.array_equal(n1, n2) and np.array_equal(v1, v2) and st1.loss == st2.loss          # deterministic gathers
+    shift = np.array([12.5, -7.25, 3.0])                                                        # exactly representable
+    shifted = g.init_nodes.copy()
+    shifted[:, :3] += shift.astype(np.float32)
+    st3, n3, v3 = run(shifted)
+    assert st3.tries_total == st1.tries_total and abs(st3.loss - st1.loss) <= 1e-4 * st1.loss
+    assert np.abs((n3[:, :3] - shift) - n1[:, :3]).max() < 2e-3                                 # float32 state at |t| ~ 60 m
+    assert np.abs(n3[:, 3:] - n1[:, 3:]).max() < 1e-5 and np.abs(v3 - v1).max() < 1e-3
+    ref = po.SparseLM(g, np.float64).run(steps=10)
+    s.set_state(g.init_nodes, g.init_vels)
+    s.lm_reset(radius=g.radius, max_steps=10, use_scheduler=0)
+    s.lm_run()
+    n, _ = s.align(g.init_nodes[0])
+    rn, _ = ref.aligned(g.init_nodes[0])
+    err = po.rel_pose_error(n.cpu().numpy(), rn)
+    assert err['rel'] <= 1e-5, err
