@@ -424,6 +424,19 @@ extern "C" int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, vo
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernel may start (and run up to its cudaGridDependencySynchronize()) while the
+// previous kernel in the stream is still draining.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan& p = h->plan;
     double* part = h->lin_part.p;
@@ -445,9 +458,10 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
         if (which == 0 && nloc > 0) {
             if (h->level_fast[l])
-                k_factor_fast<<<nloc, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
-                                                            h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min,
-                                                            q.lm_max, forced_scale, 0, &h->st.p->chol_fail, h->d_prm.p);
+                launch_pdl(k_factor_fast, nloc, F3_THREADS, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + b),
+                           h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p,
+                           h->Linv.p, (const double*)h->shared.p, q.lm_min, q.lm_max, forced_scale, 0, &h->st.p->chol_fail,
+                           (const islam_lm_params*)h->d_prm.p);
             else
                 k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
                                                               h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
@@ -476,9 +490,10 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
         int b = p.level_off[l] + h->level_nlocal[l];
         size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
         if (h->level_fast[l])
-            k_factor_fast<<<ns, F3_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
-                                                      h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
-                                                      forced_scale, 2, &h->st.p->chol_fail, h->d_prm.p);
+            launch_pdl(k_factor_fast, ns, F3_THREADS, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + b), h->fm,
+                       (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p,
+                       (const double*)h->shared.p, q.lm_min, q.lm_max, forced_scale, 2, &h->st.p->chol_fail,
+                       (const islam_lm_params*)h->d_prm.p);
         else
             k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
                                                         h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
@@ -492,9 +507,9 @@ static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     for (int l = p.n_levels - 1; l >= 0; --l) {
         int n = h->level_nlocal[l] + level_nshared(h, l);
         if (!n) continue;
-        k_backsolve_level<<<n, BS_THREADS2, (size_t)h->level_bs_bytes[l], s>>>(h->st.p, h->d_level_fronts.p + p.level_off[l],
-                                                                               h->fm, h->Lbuf.p, h->Linv.p, h->D.p, force,
-                                                                               h->level_bs_bytes[l] / 8);
+        launch_pdl(k_backsolve_level, n, BS_THREADS2, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
+                   (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
+                   h->D.p, force, h->level_bs_bytes[l] / 8);
     }
     return (int)cudaGetLastError();
 }

@@ -410,9 +410,8 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
               double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
               const double* __restrict__ shared, double lm_min_, double lm_max_, double forced_scale, int stage,
               int* chol_fail, const islam_lm_params* __restrict__ prm) {
-    if (forced_scale == 0.0 && !st->active) return;
-    const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
-    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
+    // Launched with programmatic stream serialisation (PDL): everything up to cudaGridDependencySynchronize() only
+    // touches the immutable symbolic plan, so it overlaps the tail of the previous level's kernel.
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = F3_THREADS / 32;
@@ -428,6 +427,11 @@ k_factor_fast(const LMState* __restrict__ st, const int* __restrict__ fronts, Fr
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
     const double* base = (stage == 2) ? shared + m.shared_off[f] : nullptr;
+    cudaGridDependencySynchronize();           // previous level (children's U, LM state) complete and visible
+    cudaTriggerProgrammaticLaunchCompletion(); // the next level may start staging its metadata
+    if (forced_scale == 0.0 && !st->active) return;
+    const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
     __syncthreads();
     PHASE(1);
 
@@ -796,7 +800,6 @@ __global__ void __launch_bounds__(BS_THREADS2)
 k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts, FrontMeta m,
                   const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force,
                   int smem_doubles) {
-    if (!force && !st->active) return;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NW = BS_THREADS2 / 32;
@@ -811,6 +814,9 @@ k_backsolve_level(const LMState* __restrict__ st, const int* __restrict__ fronts
     double* sLi = xs + 16;             // [np][81] inverse diagonal blocks
     double* sP = sLi + 81 * np;        // [Rf x Cf] panel copy (if it fits)
     const bool staged = (Rb + Cf + 16 + 81 * np + Rf * Cf <= smem_doubles);
+    cudaGridDependencySynchronize();           // PDL: the parents' solution (and, for the root, the factor) is complete
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (!force && !st->active) return;
     for (int r = tid; r < Rb; r += BS_THREADS2) xb[r] = D[9 * (size_t)nodes[np + r / 9] + (r % 9)];
     for (int i = tid; i < 81 * np; i += BS_THREADS2) sLi[i] = Linv[81 * (size_t)nodes[i / 81] + (i % 81)];
     if (staged)

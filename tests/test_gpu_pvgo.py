@@ -238,8 +238,7 @@ def test_run_with_scheduler_stops_like_stop_on_plateau():
 
 def test_full_size_c2_properties():
     """BASELINE config 2 at full size (5 000 poses / 49 962 factors) through size-independent properties: parity with the
-    oracle after the full 10 iterations, bitwise run-to-run determinism, and translation equivariance (every factor of
-    pvgo.py:36-51 only sees position differences, so shifting all initial positions shifts the solution and nothing else)."""
+    oracle after the full 10 iterations, bitwise run-to-run determinism, and invariance to the order of the factor list."""
     g = synth.config2()
     s = _solver(g)
 
@@ -254,13 +253,17 @@ def test_full_size_c2_properties():
     st2, n2, v2 = run(g.init_nodes)
     assert st1.steps_done == 10 and st1.tries_total == st2.tries_total
     assert np.array_equal(n1, n2) and np.array_equal(v1, v2) and st1.loss == st2.loss          # deterministic gathers
-    shift = np.array([12.5, -7.25, 3.0])                                                        # exactly representable
-    shifted = g.init_nodes.copy()
-    shifted[:, :3] += shift.astype(np.float32)
-    st3, n3, v3 = run(shifted)
-    assert st3.tries_total == st1.tries_total and abs(st3.loss - st1.loss) <= 1e-4 * st1.loss
-    assert np.abs((n3[:, :3] - shift) - n1[:, :3]).max() < 2e-3                                 # float32 state at |t| ~ 60 m
-    assert np.abs(n3[:, 3:] - n1[:, 3:]).max() < 1e-5 and np.abs(v3 - v1).max() < 1e-3
+    # the factor list is a set: a random permutation of the VO edges (links and measurements together) changes the
+    # symbolic bookkeeping and every summation order, not the problem
+    perm = np.random.default_rng(5).permutation(g.E)
+    g2 = synth.config2()
+    g2.links, g2.vo_motions = g.links[perm], g.vo_motions[perm]
+    s2 = _solver(g2)
+    s2.lm_reset(radius=g.radius, max_steps=10, use_scheduler=0)
+    st3 = s2.lm_run()
+    n3, v3 = [t.cpu().numpy().astype(np.float64) for t in s2.get_state()]
+    assert st3.tries_total == st1.tries_total and abs(st3.loss - st1.loss) <= 1e-6 * st1.loss, (st3.loss, st1.loss)
+    assert np.abs(n3 - n1).max() < 1e-4 and np.abs(v3 - v1).max() < 1e-4
     ref = po.SparseLM(g, np.float64).run(steps=10)
     s.set_state(g.init_nodes, g.init_vels)
     s.lm_reset(radius=g.radius, max_steps=10, use_scheduler=0)
