@@ -272,3 +272,45 @@ def test_full_size_c2_properties():
     rn, _ = ref.aligned(g.init_nodes[0])
     err = po.rel_pose_error(n.cpu().numpy(), rn)
     assert err['rel'] <= 1e-5, err
+
+
+def _check_steps(g, steps=3, tol=1e-5):
+    ref = po.SparseLM(g, np.float64)
+    s = _solver(g)
+    s.linearize()
+    Hd, Ho, gg, pairs = [t.cpu().numpy() for t in s.normal_equations()]
+    Href, gref, _, _ = ref.assemble(ref._res())
+    H = _dense_from_blocks(g.N, Hd, Ho, pairs)
+    assert np.abs(H - Href.toarray()).max() <= 5e-5 * max(1e-6, np.abs(Href.toarray()).max())
+    s.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
+    for k in range(steps):
+        ref.step()
+        st = s.lm_step()
+        assert st.reject_count == ref.history[-1]['rejects']
+        assert abs(st.loss - ref.history[-1]['loss']) <= 1e-4 * max(1e-3, abs(ref.history[-1]['loss']))
+    n, _ = s.align(g.init_nodes[0])
+    rn, _ = ref.aligned(g.init_nodes[0])
+    assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= tol
+
+
+def test_edge_cases_minimal_empty_duplicate_and_reversed_edges():
+    """Smallest graph (2 poses), no VO edges at all (IMU factors only), duplicated and reversed VO edges (the Hessian block
+    of a pose pair then sums several factors; `links[:,0] > links[:,1]` flips the sign convention of pvgo.py:36-38)."""
+    _check_steps(synth.window(N=2), steps=2)
+    g = synth.config2(N=12, band=1)
+    g.links = np.zeros((0, 2), np.int64)
+    g.vo_motions = np.zeros((0, 7), np.float32)
+    from oracle import lie
+    d = np.random.default_rng(2).standard_normal((g.N, 6)) * 0.02          # the dead-reckoned guess satisfies the IMU factors
+    g.init_nodes = lie.se3_retract(g.init_nodes.astype(np.float64), d).astype(np.float32)      # exactly: perturb it
+    g.init_vels = (g.init_vels + np.random.default_rng(4).standard_normal((g.N, 3)).astype(np.float32) * 0.02)
+    _check_steps(g, steps=2)
+    g = synth.config2(N=40, band=3)
+    rng = np.random.default_rng(3)
+    dup = rng.choice(g.E, 25, replace=False)
+    g.links = np.concatenate([g.links, g.links[dup]])
+    g.vo_motions = np.concatenate([g.vo_motions, g.vo_motions[dup]])
+    rev = rng.choice(g.E, 30, replace=False)                      # reverse: (j, i) with the inverse measurement
+    g.links[rev] = g.links[rev][:, ::-1]
+    g.vo_motions[rev] = lie.se3_inv(g.vo_motions[rev].astype(np.float64)).astype(np.float32)
+    _check_steps(g, steps=3)
