@@ -1,0 +1,232 @@
+// Dense root of the elimination tree: the Schur complement onto the loop-closure endpoints.
+//
+// Loop-closure edges (|i-j| > band_max) make their endpoints the last poses to be eliminated (symbolic.cpp).  With a
+// handful of closures the root is an ordinary front; with thousands (BASELINE config 4: 2 000 closures => ~4 000 poses,
+// 36 000 unknowns) it is THE dense contraction of this path (north_star: "the dense Schur-complement GEMM where it
+// genuinely is a contraction").  It is stored as one column-major (n+1) x n panel — lower triangle plus the rhs row, like
+// every other front — and factored by a tiled right-looking float64 Cholesky: per 64-column block a single-CTA diagonal
+// factorisation, a row-parallel triangular solve of the panel below, and a 64x64-tiled SYRK/GEMM update of the trailing
+// matrix (the bulk: n^3/3 flops on the fp64 pipes of all 148 SMs).  The back-substitution walks the blocks in reverse.
+// Children scatter their update matrices with float64 atomics (the only non-deterministic summation order in the
+// library: a closure pose collects contributions from both chain neighbours and every closure it takes part in).
+#pragma once
+#include "common.cuh"
+
+namespace islam {
+
+constexpr int DR_NB = 64;
+
+struct RootView {
+    double* R;            // (n+1) x n column-major, ld = n + 1
+    int n, ld, K;
+    const int* nodes;     // [K] poses of the root in elimination order
+    const int* pr_pid;    // root pairs: H block id
+    const int* pr_row;    // slot of the row pose (row slot > col slot)
+    const int* pr_col;
+    const int* pr_tr;     // 1: element (a,b) is Ho[pid][b][a]
+    int npairs;
+    const int* children;  // fronts whose parent is the root
+    int nchildren;
+    const int* root_slot; // [N]
+};
+
+// diagonal blocks (clamped + damped, A.4), rhs row and the H blocks between root poses; one warp per 9x9 block
+__global__ void __launch_bounds__(128)
+k_root_orig(const LMState* __restrict__ st, RootView rv, const double* __restrict__ Hd, const double* __restrict__ Ho,
+            const double* __restrict__ g, const islam_lm_params* __restrict__ prm, double forced_scale, double lm_min_,
+            double lm_max_) {
+    if (forced_scale == 0.0 && !st->active) return;
+    const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
+    const int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (task < rv.K) {
+        const int nd = rv.nodes[task];
+        const double* ob = Hd + 81 * (size_t)nd;
+        for (int e = lane; e < 81; e += 32) {
+            int b = e / 9, a = e - 9 * b;
+            double v = ob[9 * a + b];
+            if (a == b) v = fmin(fmax(v, lm_min), lm_max) * scale;
+            if (a >= b) atomicAdd(&rv.R[(9 * task + a) + (size_t)(9 * task + b) * rv.ld], v);
+        }
+        if (lane < 9) atomicAdd(&rv.R[rv.n + (size_t)(9 * task + lane) * rv.ld], -g[9 * (size_t)nd + lane]);
+    } else if (task < rv.K + rv.npairs) {
+        const int p = task - rv.K;
+        const double* ob = Ho + 81 * (size_t)rv.pr_pid[p];
+        const int r0 = 9 * rv.pr_row[p], c0 = 9 * rv.pr_col[p], tr = rv.pr_tr[p];
+        for (int e = lane; e < 81; e += 32) {
+            int b = e / 9, a = e - 9 * b;
+            atomicAdd(&rv.R[(r0 + a) + (size_t)(c0 + b) * rv.ld], tr ? ob[9 * b + a] : ob[9 * a + b]);
+        }
+    }
+}
+
+// extend-add of the children's update matrices (one CTA per child)
+__global__ void __launch_bounds__(256)
+k_root_children(const LMState* __restrict__ st, RootView rv, FrontMeta m, const double* __restrict__ Ubuf, int force) {
+    if (!force && !st->active) return;
+    const int c = rv.children[blockIdx.x];
+    const int nbc = m.nb[c], ub = 9 * nbc + 1;
+    const int* bnodes = m.nodes + m.nodes_off[c] + m.np[c];
+    const double* U = Ubuf + m.Uoff[c];
+    __shared__ int rmap[1024];
+    for (int r = threadIdx.x; r < ub && r < 1024; r += blockDim.x)
+        rmap[r] = (r == ub - 1) ? rv.n : 9 * rv.root_slot[bnodes[r / 9]] + r % 9;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ub * ub; idx += blockDim.x) {
+        int s = idx / ub, r = idx - s * ub;
+        if (r < s || (r == ub - 1 && s == ub - 1)) continue;
+        int rr = r < 1024 ? rmap[r] : ((r == ub - 1) ? rv.n : 9 * rv.root_slot[bnodes[r / 9]] + r % 9);
+        int cc = s < 1024 ? rmap[s] : 9 * rv.root_slot[bnodes[s / 9]] + s % 9;
+        atomicAdd(&rv.R[rr + (size_t)cc * rv.ld], U[r + (size_t)s * ub]);
+    }
+}
+
+// Cholesky of the nbk x nbk diagonal block at k0 (single CTA, shared memory)
+__global__ void __launch_bounds__(256)
+k_root_potrf(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force, int* chol_fail) {
+    if (!force && !st->active) return;
+    __shared__ double A[DR_NB][DR_NB + 1];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nbk * nbk; idx += 256) {
+        int j = idx / nbk, i = idx - j * nbk;
+        A[i][j] = (i >= j) ? rv.R[(k0 + i) + (size_t)(k0 + j) * rv.ld] : 0.0;
+    }
+    __syncthreads();
+    bool ok = true;
+    for (int k = 0; k < nbk; ++k) {
+        double d = A[k][k];
+        if (!(d > 0.0) || !(d < 1e300)) { ok = false; d = 1.0; }
+        const double inv = 1.0 / sqrt(d);
+        __syncthreads();
+        for (int i = k + tid; i < nbk; i += 256) A[i][k] = (i == k) ? d * inv : A[i][k] * inv;
+        __syncthreads();
+        const int m_ = nbk - k - 1;
+        for (int idx = tid; idx < m_ * m_; idx += 256) {
+            int j = idx / m_, i = idx - j * m_;
+            if (i >= j) A[k + 1 + i][k + 1 + j] -= A[k + 1 + i][k] * A[k + 1 + j][k];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nbk * nbk; idx += 256) {
+        int j = idx / nbk, i = idx - j * nbk;
+        if (i >= j) rv.R[(k0 + i) + (size_t)(k0 + j) * rv.ld] = A[i][j];
+    }
+    if (!ok && tid == 0) *chol_fail = 1;
+}
+
+// rows below the diagonal block (including the rhs row): X = A L_kk^-T, 128 rows per CTA
+__global__ void __launch_bounds__(128)
+k_root_trsm(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force) {
+    if (!force && !st->active) return;
+    extern __shared__ double sm[];
+    double* L = sm;                          // [nbk][nbk+1] row-major lower
+    double* X = sm + DR_NB * (DR_NB + 1);    // [nbk][128]   column c of this CTA's rows
+    const int tid = threadIdx.x;
+    const int row = k0 + nbk + blockIdx.x * 128 + tid;
+    for (int idx = tid; idx < nbk * nbk; idx += 128) {
+        int j = idx / nbk, i = idx - j * nbk;
+        L[i * (DR_NB + 1) + j] = (i >= j) ? rv.R[(k0 + i) + (size_t)(k0 + j) * rv.ld] : 0.0;
+    }
+    const bool valid = row <= rv.n;
+    for (int c = 0; c < nbk; ++c) X[c * 128 + tid] = valid ? rv.R[row + (size_t)(k0 + c) * rv.ld] : 0.0;
+    __syncthreads();
+    for (int c = 0; c < nbk; ++c) {
+        double s = X[c * 128 + tid];
+        for (int k = 0; k < c; ++k) s -= X[k * 128 + tid] * L[c * (DR_NB + 1) + k];
+        X[c * 128 + tid] = s / L[c * (DR_NB + 1) + c];
+    }
+    if (valid)
+        for (int c = 0; c < nbk; ++c) rv.R[row + (size_t)(k0 + c) * rv.ld] = X[c * 128 + tid];
+}
+
+// trailing update C -= A_i A_j^T over 64x64 tiles of the lower triangle (rows up to and including the rhs row)
+__global__ void __launch_bounds__(256)
+k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force) {
+    if (!force && !st->active) return;
+    extern __shared__ __align__(16) double sm_syrk[];
+    double (*As)[DR_NB] = reinterpret_cast<double (*)[DR_NB]>(sm_syrk);                    // [k][row]
+    double (*Bs)[DR_NB] = reinterpret_cast<double (*)[DR_NB]>(sm_syrk + DR_NB * DR_NB);
+    const int t = blockIdx.x;
+    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while ((long long)ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - (int)((long long)ti * (ti + 1) / 2);
+    const int base = k0 + nbk;
+    const int r0 = base + 64 * ti, c0 = base + 64 * tj;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 64 * nbk; idx += 256) {
+        int k = idx >> 6, r = idx & 63;
+        As[k][r] = (r0 + r <= rv.n) ? rv.R[(r0 + r) + (size_t)(k0 + k) * rv.ld] : 0.0;
+        Bs[k][r] = (c0 + r < rv.n) ? rv.R[(c0 + r) + (size_t)(k0 + k) * rv.ld] : 0.0;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;              // rows 4*tx.., cols 4*ty..
+    double acc[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < nbk; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&As[k][4 * tx]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&As[k][4 * tx + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][4 * ty]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][4 * ty + 2]);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+    }
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        const int c = c0 + 4 * ty + y;
+        if (c >= rv.n) continue;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int r = r0 + 4 * tx + x;
+            if (r <= rv.n && r >= c) rv.R[r + (size_t)c * rv.ld] -= acc[x][y];
+        }
+    }
+}
+
+// backward substitution of one block: x_blk = L_kk^-T (y_blk - L[below, blk]^T x_below)
+__global__ void __launch_bounds__(256)
+k_root_back(const LMState* __restrict__ st, RootView rv, int k0, int nbk, double* __restrict__ x, int force) {
+    if (!force && !st->active) return;
+    __shared__ double t[DR_NB];
+    __shared__ double L[DR_NB][DR_NB + 1];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int idx = tid; idx < nbk * nbk; idx += 256) {
+        int j = idx / nbk, i = idx - j * nbk;
+        L[i][j] = (i >= j) ? rv.R[(k0 + i) + (size_t)(k0 + j) * rv.ld] : 0.0;
+    }
+    for (int c = w; c < nbk; c += 8) {
+        const double* col = rv.R + (size_t)(k0 + c) * rv.ld;
+        double s = 0.0;
+        for (int r = k0 + nbk + lane; r < rv.n; r += 32) s += col[r] * x[r];
+        s = warp_sum(s);
+        if (lane == 0) t[c] = col[rv.n] - s;             // rhs row = y
+    }
+    __syncthreads();
+    if (w == 0) {
+        for (int c = nbk - 1; c >= 0; --c) {
+            double xc = t[c] / L[c][c];
+            __syncwarp();
+            if (lane == 0) t[c] = xc;
+            for (int k = lane; k < c; k += 32) t[k] -= L[c][k] * xc;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < nbk; c += 256) x[k0 + c] = t[c];
+}
+
+__global__ void k_root_scatter(const LMState* __restrict__ st, RootView rv, const double* __restrict__ x, double* __restrict__ D,
+                               int force) {
+    if (!force && !st->active) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rv.n) D[9 * (size_t)rv.nodes[i / 9] + (i % 9)] = x[i];
+}
+
+}  // namespace islam

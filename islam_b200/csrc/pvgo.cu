@@ -1,10 +1,12 @@
 // libislam_pvgo.so — handle, workspace and C ABI of the PVGO back-end (see include/islam_pvgo.h).
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "common.cuh"
+#include "dense_root.cuh"
 #include "lie.cuh"
 #include "linearize.cuh"
 #include "lm.cuh"
@@ -166,7 +168,10 @@ struct islam_pvgo {
     DevBuf<int> d_np, d_nb, d_nodes_off, d_nodes, d_child_off, d_children, d_cinv_off, d_cinv, d_hmap_off, d_hmap,
         d_part, d_level_fronts, d_shared_fronts;
     DevBuf<long long> d_Loff, d_Uoff, d_shared_off;
-    DevBuf<double> Lbuf, Ubuf, Linv, shared;
+    DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
+    DevBuf<int> d_root_nodes, d_root_pid, d_root_row, d_root_col, d_root_tr, d_root_children, d_root_slot;
+    RootView rv;
+    bool has_root = false;
     DevBuf<LMState> st;
     DevBuf<islam_lm_params> d_prm;
     DevBuf<double> d_w;
@@ -193,7 +198,9 @@ struct islam_pvgo {
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot};
         for (auto* b : fb) b->release();
-        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared};
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x};
+        DevBuf<int>* rb[] = {&d_root_nodes, &d_root_pid, &d_root_row, &d_root_col, &d_root_tr, &d_root_children, &d_root_slot};
+        for (auto* b : rb) b->release();
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_shared_off.release();
         st.release(); d_prm.release(); d_w.release();
@@ -232,7 +239,8 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     // Loop-closure endpoints are eliminated last as one dense root; the dedicated tiled dense-root path (needed for
     // BASELINE config 4: 2 000 closures => ~4 000 root poses) is not implemented yet, so refuse instead of asking
     // cudaMalloc for terabytes of update matrices.
-    if (p.root_pivots > 256 || p.U_doubles + p.L_doubles > (1LL << 34)) { delete h; return -7; }
+    if (p.U_doubles + p.L_doubles > (1LL << 34)) { delete h; return -7; }     // > 128 GB of fp64 panels
+    if (p.dense_root >= 0 && opts.n_parts > 1) { delete h; return -6; }         // dense root: single GPU only for now
     islam_lm_default_params(&h->prm);
 
 #define UP(buf, vec) do { cudaError_t _e = h->buf.upload(vec); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
@@ -284,6 +292,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             std::vector<int> loc, shr;
             for (int k = b; k < e; ++k) {
                 int f = p.level_fronts[k];
+                if (f == p.dense_root) continue;                    // factored by the dense-root kernels
                 if (opts.n_parts > 1 && p.f_part[f] < 0) shr.push_back(f);
                 else if (opts.n_parts == 1 || p.f_part[f] == opts.part) loc.push_back(f);
             }
@@ -327,6 +336,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     h->level_bs_bytes.assign(p.n_levels, 0);
     h->level_fast.assign(p.n_levels, 1);
     for (int f = 0; f < p.F; ++f) {
+        if (f == p.dense_root) continue;
         int l = p.f_level[f];
         long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
         int nch = p.f_child_off[f + 1] - p.f_child_off[f];
@@ -361,6 +371,37 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.child_off = h->d_child_off.p; fm.children = h->d_children.p;
     fm.cinv_off = h->d_cinv_off.p; fm.cinv = h->d_cinv.p; fm.hmap_off = h->d_hmap_off.p; fm.hmap = h->d_hmap.p;
     fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p; fm.mypart = opts.part;
+    // dense root (loop-closure Schur complement)
+    if (p.dense_root >= 0) {
+        const int fr = p.dense_root, K = p.f_np[fr];
+        std::vector<int> rnodes(p.f_nodes.begin() + p.f_nodes_off[fr], p.f_nodes.begin() + p.f_nodes_off[fr] + K);
+        std::vector<int> pid, prow, pcol, ptr_, kids;
+        for (int i = 0; i < p.P; ++i) {
+            int a = p.root_slot[p.pair_lo[i]], b = p.root_slot[p.pair_hi[i]];
+            if (a < 0 || b < 0) continue;
+            // Ho[i] = H[lo dofs, hi dofs]; the block lands at (row slot > col slot)
+            if (a > b) { pid.push_back(i); prow.push_back(a); pcol.push_back(b); ptr_.push_back(0); }
+            else { pid.push_back(i); prow.push_back(b); pcol.push_back(a); ptr_.push_back(1); }
+        }
+        for (int k = p.f_child_off[fr]; k < p.f_child_off[fr + 1]; ++k) kids.push_back(p.f_children[k]);
+        cudaError_t e1 = h->d_root_nodes.upload(rnodes);
+        if (e1 == cudaSuccess) e1 = h->d_root_pid.upload(pid);
+        if (e1 == cudaSuccess) e1 = h->d_root_row.upload(prow);
+        if (e1 == cudaSuccess) e1 = h->d_root_col.upload(pcol);
+        if (e1 == cudaSuccess) e1 = h->d_root_tr.upload(ptr_);
+        if (e1 == cudaSuccess) e1 = h->d_root_children.upload(kids);
+        if (e1 == cudaSuccess) e1 = h->d_root_slot.upload(p.root_slot);
+        if (e1 == cudaSuccess) e1 = h->root_x.alloc(9 * (size_t)K + 1);
+        if (e1 != cudaSuccess) { delete h; return (int)e1; }
+        RootView& rv = h->rv;
+        rv.R = h->Lbuf.p + p.f_Loff[fr]; rv.n = 9 * K; rv.ld = 9 * K + 1; rv.K = K;
+        rv.nodes = h->d_root_nodes.p; rv.pr_pid = h->d_root_pid.p; rv.pr_row = h->d_root_row.p; rv.pr_col = h->d_root_col.p;
+        rv.pr_tr = h->d_root_tr.p; rv.npairs = (int)pid.size(); rv.children = h->d_root_children.p;
+        rv.nchildren = (int)kids.size(); rv.root_slot = h->d_root_slot.p;
+        h->has_root = true;
+        cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128)));
+        cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * DR_NB * DR_NB));
+    }
     // LM state
     LMState s;
     std::memset(&s, 0, sizeof(s));
@@ -449,6 +490,9 @@ static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
     return (int)cudaGetLastError();
 }
 
+static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale);
+static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force);
+
 static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int which /*0 local, 2 shared*/) {
     const Plan& p = h->plan;
     const islam_lm_params& q = h->prm;
@@ -468,6 +512,44 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int
                                                               forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail, h->d_prm.p);
         }
     }
+    if (which == 0) { int rc = launch_root_factor(h, s, forced_scale); if (rc) return rc; }
+    return (int)cudaGetLastError();
+}
+
+// ---- dense root: tiled right-looking Cholesky of the loop-closure Schur complement, then its back-substitution ----------
+static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
+    if (!h->has_root) return 0;
+    const RootView& rv = h->rv;
+    const islam_lm_params& q = h->prm;
+    const int force = forced_scale != 0.0;
+    CK(cudaMemsetAsync(rv.R, 0, sizeof(double) * (size_t)rv.ld * rv.n, s));
+    int tasks = rv.K + rv.npairs;
+    k_root_orig<<<(tasks * 32 + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min, q.lm_max);
+    if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force);
+    for (int k0 = 0; k0 < rv.n; k0 += DR_NB) {
+        int nbk = std::min(DR_NB, rv.n - k0);
+        k_root_potrf<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, force, &h->st.p->chol_fail);
+        int below = rv.n + 1 - (k0 + nbk);                      // rows below, including the rhs row
+        if (below > 0)
+            k_root_trsm<<<(below + 127) / 128, 128, sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128), s>>>(h->st.p, rv, k0, nbk, force);
+        if (k0 + nbk < rv.n) {
+            long long T = (below + 63) / 64;
+            long long ntiles = T * (T + 1) / 2;
+            k_root_syrk<<<(unsigned)ntiles, 256, sizeof(double) * 2 * DR_NB * DR_NB, s>>>(h->st.p, rv, k0, nbk, force);
+        }
+    }
+    return (int)cudaGetLastError();
+}
+
+static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force) {
+    if (!h->has_root) return 0;
+    const RootView& rv = h->rv;
+    int nblk = (rv.n + DR_NB - 1) / DR_NB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        int k0 = b * DR_NB, nbk = std::min(DR_NB, rv.n - k0);
+        k_root_back<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, h->root_x.p, force);
+    }
+    k_root_scatter<<<(rv.n + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->root_x.p, h->D.p, force);
     return (int)cudaGetLastError();
 }
 
@@ -504,6 +586,7 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
 
 static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan& p = h->plan;
+    { int rc = launch_root_solve(h, s, force); if (rc) return rc; }
     for (int l = p.n_levels - 1; l >= 0; --l) {
         int n = h->level_nlocal[l] + level_nshared(h, l);
         if (!n) continue;

@@ -129,7 +129,11 @@ int build_plan(int N, int E, const int64_t* links, const SymbolicOpts& opts, Pla
         for (int n = 0; n < N; ++n)
             if (is_root[n]) root.push_back(n);
         p.root_pivots = (int)root.size();
-        if (!root.empty()) bld.emit(std::move(root), -1);
+        if ((int)root.size() >= opts.dense_root_min) {          // one dense front, factored by the tiled dense path
+            p.dense_root = (int)bld.fronts.size();
+            bld.fronts.emplace_back(root);
+            bld.parts.push_back(-1);
+        } else if (!root.empty()) bld.emit(std::move(root), -1);
     }
     p.F = (int)bld.fronts.size();
     p.f_part = bld.parts;
@@ -191,7 +195,7 @@ int build_plan(int N, int E, const int64_t* links, const SymbolicOpts& opts, Pla
         p.n_levels = std::max(p.n_levels, p.f_level[f] + 1);
         p.f_child_off[f + 1] = p.f_child_off[f] + (int)children[f].size();
         p.f_children.insert(p.f_children.end(), children[f].begin(), children[f].end());
-        p.f_hmap_off[f + 1] = p.f_hmap_off[f] + (np + nb) * np;
+        p.f_hmap_off[f + 1] = p.f_hmap_off[f] + (f == p.dense_root ? 0 : (np + nb) * np);
     }
     // inverse child maps and H gather maps
     p.c_inv_off.assign(p.f_children.size() + 1, 0);
@@ -203,6 +207,7 @@ int build_plan(int N, int E, const int64_t* links, const SymbolicOpts& opts, Pla
         for (int s = 0; s < ns; ++s) slot_in[nodes[s]] = s;
         for (int k = p.f_child_off[f]; k < p.f_child_off[f + 1]; ++k) {
             int c = p.f_children[k];
+            if (f == p.dense_root) { p.c_inv_off[k + 1] = p.c_inv_off[k]; continue; }   // children are pushed, not pulled
             p.c_inv_off[k + 1] = p.c_inv_off[k] + ns;
             size_t base = p.c_inv.size();
             p.c_inv.resize(base + ns, -1);
@@ -213,8 +218,8 @@ int build_plan(int N, int E, const int64_t* links, const SymbolicOpts& opts, Pla
                 p.c_inv[base + s] = b;
             }
         }
-        int* hm = &p.hmap[p.f_hmap_off[f]];
-        for (int cs = 0; cs < np; ++cs) {
+        int* hm = p.hmap.data() + p.f_hmap_off[f];
+        for (int cs = 0; cs < np && f != p.dense_root; ++cs) {
             int nc = nodes[cs];
             for (int q : adj[nc]) {
                 int rs = slot_in[q];
@@ -228,6 +233,9 @@ int build_plan(int N, int E, const int64_t* links, const SymbolicOpts& opts, Pla
         }
         for (int s = 0; s < ns; ++s) slot_in[nodes[s]] = -1;
     }
+    p.root_slot.assign(N, -1);
+    if (p.dense_root >= 0)
+        for (int k = 0; k < p.f_np[p.dense_root]; ++k) p.root_slot[p.f_nodes[p.f_nodes_off[p.dense_root] + k]] = k;
     // level schedule
     p.level_off.assign(p.n_levels + 1, 0);
     for (int f = 0; f < p.F; ++f) p.level_off[p.f_level[f] + 1]++;

@@ -20,6 +20,7 @@ struct SymbolicOpts {
     int leaf_max = 8;    // poses per leaf front
     int pivot_max = 8;   // poses eliminated per front (9*pivot_max columns)
     int n_parts = 1;     // multi-GPU: number of contiguous pose windows (power of two)
+    int dense_root_min = 33;   // loop-closure roots with at least this many poses become ONE dense front (dense_root.cuh)
 };
 
 struct Plan {
@@ -43,6 +44,8 @@ struct Plan {
     std::vector<int> node_front, node_slot, node_pos;  // owner front / slot / elimination position
     long long L_doubles = 0, U_doubles = 0;
     int n_levels = 0, max_rows = 0, max_cols = 0, root_pivots = 0;
+    int dense_root = -1;                                // front id of the dense root, or -1
+    std::vector<int> root_slot;                         // [N] slot of a pose inside the dense root, or -1
     double factor_flops = 0;                            // multiply-adds of one numeric factorisation
 };
 
