@@ -16,7 +16,7 @@ ap.add_argument('--leaf', type=int, default=0)
 ap.add_argument('--pivot', type=int, default=0)
 a = ap.parse_args()
 g = {'C1': synth.config1, 'C2': synth.config2, 'C3': synth.config3, 'win9': synth.window,
-     'C4s': lambda: synth.config4(N=5000, n_lc=20)}[a.config]()
+     'C4s': lambda: synth.config4(N=5000, n_lc=20), 'C4': synth.config4}[a.config]()
 t0 = time.time()
 s = PVGOSolver(g.N, g.links, leaf_max=a.leaf, pivot_max=a.pivot)
 d = s.dims
