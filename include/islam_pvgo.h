@@ -141,8 +141,9 @@ int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles
 int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream);
 int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
 int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
-/* owner window of every pose (host array of N int32): >= 0 private to that rank, -1 shared / replicated */
-int islam_pvgo_node_parts(const islam_pvgo* h, int32_t* out_host);
+/* owner window of every 3-dof variable (host array of 3N int32, [tau, phi, v] per pose): >= 0 private to that rank,
+ * -1 shared / replicated (solved redundantly on every rank) */
+int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host);
 
 /* ---- outer losses and gauge alignment ------------------------------------------------------------------ */
 /* vo_loss (pvgo.py:67-78) at the current nodes (detached) for arbitrary vo_motions P (E x 7):

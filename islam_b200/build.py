@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libislam_pvgo.so')
-SOURCES = ['pvgo.cu', 'imu.cu', 'lieops.cu', 'symbolic.cpp']
+SOURCES = ['pvgo.cu', 'imu.cu', 'lieops.cu', 'symbolic.cpp', 'symbolic3.cpp']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 
@@ -31,12 +31,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, phase_clocks=False):
+    """phase_clocks: developer build (lib/libislam_dbg.so) whose factor kernel stamps clock64() per phase (tools/phase_clocks.py)."""
+    out = LIB.replace('libislam_pvgo.so', 'libislam_dbg.so') if phase_clocks else LIB
+    if not force and not phase_clocks and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [_nvcc(), '-O3', '-std=c++17', *ARCH, '-lineinfo', '-Xcompiler', '-fPIC', '-shared',
-           '-diag-suppress', '177', '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           '-diag-suppress', '177', '-o', out] + (['-DISLAM_PHASE_CLOCKS'] if phase_clocks else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, '-Xptxas'); cmd.insert(2, '-v')
         print(' '.join(cmd))
@@ -45,8 +48,8 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, phase_clocks='--phase-clocks' in sys.argv))

@@ -9,20 +9,24 @@ namespace islam {
 
 typedef islam_lm_state LMState;
 
-// Device views of the symbolic plan (symbolic.h), uploaded once per graph.
-struct FrontMeta {
-    const int* np;          // [F] pivot poses
-    const int* nb;          // [F] boundary poses
-    const int* nodes_off;   // [F+1]
-    const int* nodes;       // pivots then boundary (elimination order)
-    const long long* Loff;  // [F] offset of the (9(np+nb)+1) x 9np column-major panel
-    const long long* Uoff;  // [F] offset of the (9nb+1)^2 column-major update matrix
+// Device views of the symbolic plan (symbolic3.h), uploaded once per graph.
+struct Front3Meta {
+    const int* np;          // [F] real pivot variables
+    const int* npad;        // [F] pivot slots (np rounded up to a multiple of 3; the extra ones are dummies)
+    const int* nb;          // [F] boundary variables
+    const int* vars_off;    // [F+1]
+    const int* vars;        // pivot slots (dummy = -1) then boundary, elimination order; variable u = 3 pose + {tau, phi, v}
+    const long long* Loff;  // [F] offset of the (3(npad+nb)+1) x 3npad column-major panel
+    const long long* Uoff;  // [F] offset of the packed lower triangle of the (3nb+1)^2 update matrix
+    const long long* Ioff;  // [F] offset of the npad/3 inverse 9x9 diagonal blocks
     const int* child_off;   // [F+1]
     const int* children;    // child front ids
-    const int* cinv_off;    // [nchildren_total+1]
-    const int* cinv;        // parent slot -> child boundary index | -1
-    const int* hmap_off;    // [F+1]
-    const int* hmap;        // (np+nb) x np : (pair<<1|transpose) | -1
+    const int* cmap_off;    // [nchildren_total+1]
+    const int* cmap;        // child boundary index -> parent slot
+    const int* orig_off;    // [F+1] original 3x3 blocks first touched by the front
+    const int* orig_rs;     // row slot
+    const int* orig_cs;     // column slot (a pivot)
+    const int* orig_src;    // (offset << 2) | (2: Ho, 0: Hd) | (1: transposed)
     const int* part;        // [F] owning window or -1 (shared)
     const long long* shared_off;  // [F] offset into the shared all-reduce buffer or -1
     int mypart;                   // this rank's window (multi-GPU)

@@ -7,6 +7,7 @@
 // every other front — and factored by a tiled right-looking float64 Cholesky: per 64-column block a single-CTA diagonal
 // factorisation, a row-parallel triangular solve of the panel below, and a 64x64-tiled SYRK/GEMM update of the trailing
 // matrix (the bulk: n^3/3 flops on the fp64 pipes of all 148 SMs).  The back-substitution walks the blocks in reverse.
+// Only the tau / phi variables of a closure pose are promoted (symbolic3.cpp): 6 unknowns per pose, not 9.
 // Children scatter their update matrices with float64 atomics (the only non-deterministic summation order in the
 // library: a closure pose collects contributions from both chain neighbours and every closure it takes part in).
 #pragma once
@@ -18,66 +19,54 @@ constexpr int DR_NB = 64;
 
 struct RootView {
     double* R;            // (n+1) x n column-major, ld = n + 1
-    int n, ld, K;
-    const int* nodes;     // [K] poses of the root in elimination order
-    const int* pr_pid;    // root pairs: H block id
-    const int* pr_row;    // slot of the row pose (row slot > col slot)
-    const int* pr_col;
-    const int* pr_tr;     // 1: element (a,b) is Ho[pid][b][a]
-    int npairs;
-    const int* children;  // fronts whose parent is the root
+    int n, ld, K;         // n = 3 K unknowns of K root variables
+    int front;            // front id of the dense root in the plan
+    const int* vars;      // [K] root variables in elimination order
+    const int* children;  // child-entry indices k (into Front3Meta::children / cmap_off) of the root's children
     int nchildren;
-    const int* root_slot; // [N]
 };
 
-// diagonal blocks (clamped + damped, A.4), rhs row and the H blocks between root poses; one warp per 9x9 block
+// original 3x3 blocks of the root (diagonal blocks clamped + damped, A.4) and the rhs row; one thread per scalar
 __global__ void __launch_bounds__(128)
-k_root_orig(const LMState* __restrict__ st, RootView rv, const double* __restrict__ Hd, const double* __restrict__ Ho,
-            const double* __restrict__ g, const islam_lm_params* __restrict__ prm, double forced_scale, double lm_min_,
-            double lm_max_) {
+k_root_orig(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Hd,
+            const double* __restrict__ Ho, const double* __restrict__ g, const islam_lm_params* __restrict__ prm,
+            double forced_scale, double lm_min_, double lm_max_) {
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
     const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
-    const int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (task < rv.K) {
-        const int nd = rv.nodes[task];
-        const double* ob = Hd + 81 * (size_t)nd;
-        for (int e = lane; e < 81; e += 32) {
-            int b = e / 9, a = e - 9 * b;
-            double v = ob[9 * a + b];
-            if (a == b) v = fmin(fmax(v, lm_min), lm_max) * scale;
-            if (a >= b) atomicAdd(&rv.R[(9 * task + a) + (size_t)(9 * task + b) * rv.ld], v);
-        }
-        if (lane < 9) atomicAdd(&rv.R[rv.n + (size_t)(9 * task + lane) * rv.ld], -g[9 * (size_t)nd + lane]);
-    } else if (task < rv.K + rv.npairs) {
-        const int p = task - rv.K;
-        const double* ob = Ho + 81 * (size_t)rv.pr_pid[p];
-        const int r0 = 9 * rv.pr_row[p], c0 = 9 * rv.pr_col[p], tr = rv.pr_tr[p];
-        for (int e = lane; e < 81; e += 32) {
-            int b = e / 9, a = e - 9 * b;
-            atomicAdd(&rv.R[(r0 + a) + (size_t)(c0 + b) * rv.ld], tr ? ob[9 * b + a] : ob[9 * a + b]);
-        }
+    const int o0 = m.orig_off[rv.front], no = m.orig_off[rv.front + 1] - o0;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 9 * no) {
+        const int e = idx / 9, k = idx - 9 * e, c = k / 3, r = k - 3 * c;
+        const int rs = m.orig_rs[o0 + e], cs = m.orig_cs[o0 + e], src = m.orig_src[o0 + e];
+        if (rs == cs && r < c) return;
+        const double* arr = (src & 2) ? Ho : Hd;
+        double v = arr[(size_t)(src >> 2) + ((src & 1) ? 9 * c + r : 9 * r + c)];
+        if (rs == cs && r == c) v = fmin(fmax(v, lm_min), lm_max) * scale;
+        atomicAdd(&rv.R[(3 * rs + r) + (size_t)(3 * cs + c) * rv.ld], v);
+    } else if (idx < 9 * no + rv.n) {
+        const int j = idx - 9 * no;
+        atomicAdd(&rv.R[rv.n + (size_t)j * rv.ld], -g[3 * (size_t)rv.vars[j / 3] + j % 3]);
     }
 }
 
-// extend-add of the children's update matrices (one CTA per child)
+// extend-add of the children's (packed) update matrices, one CTA per child
 __global__ void __launch_bounds__(256)
-k_root_children(const LMState* __restrict__ st, RootView rv, FrontMeta m, const double* __restrict__ Ubuf, int force) {
+k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Ubuf, int force) {
     if (!force && !st->active) return;
-    const int c = rv.children[blockIdx.x];
-    const int nbc = m.nb[c], ub = 9 * nbc + 1;
-    const int* bnodes = m.nodes + m.nodes_off[c] + m.np[c];
+    const int k = rv.children[blockIdx.x];
+    const int c = m.children[k];
+    const int* cm = m.cmap + m.cmap_off[k];
+    const int ub = 3 * m.nb[c] + 1;
     const double* U = Ubuf + m.Uoff[c];
-    __shared__ int rmap[1024];
-    for (int r = threadIdx.x; r < ub && r < 1024; r += blockDim.x)
-        rmap[r] = (r == ub - 1) ? rv.n : 9 * rv.root_slot[bnodes[r / 9]] + r % 9;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < ub * ub; idx += blockDim.x) {
-        int s = idx / ub, r = idx - s * ub;
-        if (r < s || (r == ub - 1 && s == ub - 1)) continue;
-        int rr = r < 1024 ? rmap[r] : ((r == ub - 1) ? rv.n : 9 * rv.root_slot[bnodes[r / 9]] + r % 9);
-        int cc = s < 1024 ? rmap[s] : 9 * rv.root_slot[bnodes[s / 9]] + s % 9;
-        atomicAdd(&rv.R[rr + (size_t)cc * rv.ld], U[r + (size_t)s * ub]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int cc = warp; cc < ub - 1; cc += 8) {
+        const int pc = 3 * cm[cc / 3] + cc % 3;
+        const double* col = U + ((size_t)cc * ub - (size_t)cc * (cc - 1) / 2 - cc);
+        for (int r = cc + lane; r < ub; r += 32) {
+            const int pr = (r == ub - 1) ? rv.n : 3 * cm[r / 3] + r % 3;
+            atomicAdd(&rv.R[pr + (size_t)pc * rv.ld], col[r]);
+        }
     }
 }
 
@@ -226,7 +215,7 @@ __global__ void k_root_scatter(const LMState* __restrict__ st, RootView rv, cons
                                int force) {
     if (!force && !st->active) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rv.n) D[9 * (size_t)rv.nodes[i / 9] + (i % 9)] = x[i];
+    if (i < rv.n) D[3 * (size_t)rv.vars[i / 3] + (i % 3)] = x[i];
 }
 
 }  // namespace islam

@@ -10,8 +10,9 @@
 #include "lie.cuh"
 #include "linearize.cuh"
 #include "lm.cuh"
-#include "solver.cuh"
+#include "solver3.cuh"
 #include "symbolic.h"
+#include "symbolic3.h"
 
 using namespace islam;
 
@@ -148,13 +149,14 @@ __global__ void k_set_state_flags(LMState* st, int cur) {
 
 // =================================================================================================================
 struct islam_pvgo {
-    Plan plan;
+    Plan plan;                      // pairs / CSR for the assembly kernels
+    Plan3 p3;                       // fronts over 3-dof variables
     islam_pvgo_opts opts;
     islam_lm_params prm;
     ProblemView pv;
     LinBuffers lb;
     AsmView av;
-    FrontMeta fm;
+    Front3Meta fm;
     // problem + state
     DevBuf<int> ei, ej, edge_owner, pair_owner;
     DevBuf<float> Z, drot, dtrans, dvel, dt;
@@ -165,11 +167,10 @@ struct islam_pvgo {
     DevBuf<double> Hd, Ho, g, D;
     // symbolic plan on the device
     DevBuf<int> d_node_eoff, d_node_edges, d_pair_lo, d_pair_hi, d_pair_adj, d_pair_eoff, d_pair_edges;
-    DevBuf<int> d_np, d_nb, d_nodes_off, d_nodes, d_child_off, d_children, d_cinv_off, d_cinv, d_hmap_off, d_hmap,
-        d_part, d_level_fronts, d_shared_fronts;
-    DevBuf<long long> d_Loff, d_Uoff, d_shared_off;
+    DevBuf<int> d_np, d_npad, d_nb, d_vars_off, d_vars, d_child_off, d_children, d_cmap_off, d_cmap, d_orig_off, d_orig_rs,
+        d_orig_cs, d_orig_src, d_part, d_level_fronts, d_shared_fronts, d_root_vars, d_root_children;
+    DevBuf<long long> d_Loff, d_Uoff, d_Ioff, d_shared_off;
     DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
-    DevBuf<int> d_root_nodes, d_root_pid, d_root_row, d_root_col, d_root_tr, d_root_children, d_root_slot;
     RootView rv;
     bool has_root = false;
     DevBuf<LMState> st;
@@ -177,10 +178,11 @@ struct islam_pvgo {
     DevBuf<double> d_w;
     LMState* st_host = nullptr;     // pinned mirror
     int nblk_vo = 0, nblk_imu = 0;
-    int max_smem_doubles = 0;
-    std::vector<int> level_smem_doubles, level_bs_bytes, level_fast;
+    // per level: kernel variant (bit 0: update matrix in shared memory, bit 1: 256-thread CTAs, two per SM),
+    // dynamic shared memory of the factor / back-substitution kernels
+    std::vector<int> level_variant, level_smem_bytes, level_bs_bytes;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
-    std::vector<int> level_nlocal;
+    std::vector<int> level_nlocal, level_nshared;
     std::vector<long long> h_shared_off;
     long long shared_doubles = 0;
     int n_shared = 0;
@@ -191,18 +193,16 @@ struct islam_pvgo {
         if (graph_try) cudaGraphExecDestroy(graph_try);
         if (st_host) cudaFreeHost(st_host);
         DevBuf<int>* ib[] = {&ei, &ej, &edge_owner, &pair_owner, &d_node_eoff, &d_node_edges, &d_pair_lo, &d_pair_hi,
-                             &d_pair_adj, &d_pair_eoff, &d_pair_edges, &d_np, &d_nb, &d_nodes_off, &d_nodes,
-                             &d_child_off, &d_children, &d_cinv_off, &d_cinv, &d_hmap_off, &d_hmap, &d_part,
-                             &d_level_fronts, &d_shared_fronts};
+                             &d_pair_adj, &d_pair_eoff, &d_pair_edges, &d_np, &d_npad, &d_nb, &d_vars_off, &d_vars,
+                             &d_child_off, &d_children, &d_cmap_off, &d_cmap, &d_orig_off, &d_orig_rs, &d_orig_cs,
+                             &d_orig_src, &d_part, &d_level_fronts, &d_shared_fronts, &d_root_vars, &d_root_children};
         for (auto* b : ib) b->release();
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot};
         for (auto* b : fb) b->release();
         DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x};
-        DevBuf<int>* rb[] = {&d_root_nodes, &d_root_pid, &d_root_row, &d_root_col, &d_root_tr, &d_root_children, &d_root_slot};
-        for (auto* b : rb) b->release();
         for (auto* b : db) b->release();
-        d_Loff.release(); d_Uoff.release(); d_shared_off.release();
+        d_Loff.release(); d_Uoff.release(); d_Ioff.release(); d_shared_off.release();
         st.release(); d_prm.release(); d_w.release();
     }
 };
@@ -218,6 +218,13 @@ extern "C" void islam_lm_default_params(islam_lm_params* p) {
     p->max_steps = 10; p->patience = 3; p->use_scheduler = 1; p->decreasing = 1e-3;   // pvgo.py:172
 }
 
+// kernel variants of one level (see islam_pvgo::level_variant)
+enum { VAR_USMEM = 1, VAR_SMALL_CTA = 2 };
+
+template <int NT, int MINB, bool U_SMEM> static void set_factor_smem(int bytes) {
+    cudaFuncSetAttribute(k_factor3<NT, MINB, U_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const int64_t* links, const islam_pvgo_opts* o) {
     if (!out || N < 2 || E < 0 || (E > 0 && !links)) return -1;
     islam_pvgo* h = new (std::nothrow) islam_pvgo();
@@ -229,18 +236,18 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     if (opts.leaf_max <= 0) opts.leaf_max = 8;
     if (opts.pivot_max <= 0) opts.pivot_max = 8;
     if (opts.n_parts <= 0) opts.n_parts = 1;
-    if (opts.part < 0 || opts.part >= opts.n_parts) { delete h; return -1; }
+    if (opts.part < 0 || opts.part >= opts.n_parts || opts.pivot_max > 21) { delete h; return -1; }   // 9 pivot_max columns <= F3_HEAD
     h->opts = opts;
     SymbolicOpts so;
     so.band_max = opts.band_max; so.leaf_max = opts.leaf_max; so.pivot_max = opts.pivot_max; so.n_parts = opts.n_parts;
     int rc = build_plan(N, E, links, so, h->plan);
+    if (!rc) rc = build_plan3(h->plan, links, so, h->p3);
     if (rc != 0) { delete h; return rc; }
-    Plan& p = h->plan;
-    // Loop-closure endpoints are eliminated last as one dense root; the dedicated tiled dense-root path (needed for
-    // BASELINE config 4: 2 000 closures => ~4 000 root poses) is not implemented yet, so refuse instead of asking
-    // cudaMalloc for terabytes of update matrices.
-    if (p.U_doubles + p.L_doubles > (1LL << 34)) { delete h; return -7; }     // > 128 GB of fp64 panels
-    if (p.dense_root >= 0 && opts.n_parts > 1) { delete h; return -6; }         // dense root: single GPU only for now
+    const Plan& p = h->plan;
+    const Plan3& q = h->p3;
+    // Loop-closure endpoints are eliminated last; from 33 closure poses on they form ONE dense root (dense_root.cuh).
+    if (q.U_doubles + q.L_doubles > (1LL << 34)) { delete h; return -7; }       // > 128 GB of fp64 panels
+    if (q.dense_root >= 0 && opts.n_parts > 1) { delete h; return -6; }          // dense root: single GPU only for now
     islam_lm_default_params(&h->prm);
 
 #define UP(buf, vec) do { cudaError_t _e = h->buf.upload(vec); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
@@ -251,17 +258,20 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         for (int e = 0; e < E; ++e) { ei[e] = (int)links[2 * e]; ej[e] = (int)links[2 * e + 1]; }
         UP(ei, ei); UP(ej, ej);
         if (opts.n_parts > 1) {
-            // a factor is owned by the window holding one of its private endpoints; all-shared factors by window 0
-            std::vector<int> node_part(N);
-            for (int n = 0; n < N; ++n) node_part[n] = p.f_part[p.node_front[n]];
+            // a factor is owned by the window holding one of the PRIVATE variables it touches (they all agree: the
+            // variables of a factor form a clique, and a separator never lets a clique straddle two windows);
+            // factors that only touch shared variables go to window 0
+            auto vpart = [&](int v) { return q.f_part[q.var_front[v]]; };
             std::vector<int> eo(E), po(p.M);
             for (int e = 0; e < E; ++e) {
-                int a = node_part[ei[e]], b = node_part[ej[e]];
-                eo[e] = a >= 0 ? a : (b >= 0 ? b : 0);
+                int own = -1;
+                for (int c = 0; c < 2; ++c) { own = std::max(own, vpart(3 * ei[e] + c)); own = std::max(own, vpart(3 * ej[e] + c)); }
+                eo[e] = own >= 0 ? own : 0;
             }
             for (int i = 0; i < p.M; ++i) {
-                int a = node_part[i], b = node_part[i + 1];
-                po[i] = a >= 0 ? a : (b >= 0 ? b : 0);
+                int own = -1;
+                for (int c = 0; c < 6; ++c) own = std::max(own, vpart(3 * i + c));
+                po[i] = own >= 0 ? own : 0;
             }
             UP(edge_owner, eo); UP(pair_owner, po);
         }
@@ -277,26 +287,28 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     AL(Hd, 81 * (size_t)N); AL(Ho, 81 * (size_t)p.P); AL(g, 9 * (size_t)N); AL(D, 9 * (size_t)N);
     UP(d_node_eoff, p.node_eoff); UP(d_node_edges, p.node_edges); UP(d_pair_lo, p.pair_lo); UP(d_pair_hi, p.pair_hi);
     UP(d_pair_adj, p.pair_adj); UP(d_pair_eoff, p.pair_eoff); UP(d_pair_edges, p.pair_edges);
-    UP(d_np, p.f_np); UP(d_nb, p.f_nb); UP(d_nodes_off, p.f_nodes_off); UP(d_nodes, p.f_nodes);
-    UP(d_child_off, p.f_child_off); UP(d_children, p.f_children); UP(d_cinv_off, p.c_inv_off); UP(d_cinv, p.c_inv);
-    UP(d_hmap_off, p.f_hmap_off); UP(d_hmap, p.hmap); UP(d_part, p.f_part);
-    UP(d_Loff, p.f_Loff); UP(d_Uoff, p.f_Uoff);
+    UP(d_np, q.f_np); UP(d_npad, q.f_npad); UP(d_nb, q.f_nb); UP(d_vars_off, q.f_vars_off); UP(d_vars, q.f_vars);
+    UP(d_child_off, q.f_child_off); UP(d_children, q.f_children); UP(d_cmap_off, q.c_map_off); UP(d_cmap, q.c_map);
+    UP(d_orig_off, q.f_orig_off); UP(d_orig_rs, q.orig_rs); UP(d_orig_cs, q.orig_cs); UP(d_orig_src, q.orig_src);
+    UP(d_part, q.f_part); UP(d_Loff, q.f_Loff); UP(d_Uoff, q.f_Uoff); UP(d_Ioff, q.f_Ioff);
     // level lists: local fronts first, shared fronts last (multi-GPU: local = fronts of this rank's window)
     {
-        std::vector<int> lf = p.level_fronts;
-        h->level_nlocal.assign(p.n_levels, 0);
-        h->h_shared_off.assign(p.F, -1);
+        std::vector<int> lf = q.level_fronts;
+        h->level_nlocal.assign(q.n_levels, 0);
+        h->level_nshared.assign(q.n_levels, 0);
+        h->h_shared_off.assign(q.F, -1);
         std::vector<int> shared_list;
-        for (int l = 0; l < p.n_levels; ++l) {
-            int b = p.level_off[l], e = p.level_off[l + 1];
+        for (int l = 0; l < q.n_levels; ++l) {
+            int b = q.level_off[l], e = q.level_off[l + 1];
             std::vector<int> loc, shr;
             for (int k = b; k < e; ++k) {
-                int f = p.level_fronts[k];
-                if (f == p.dense_root) continue;                    // factored by the dense-root kernels
-                if (opts.n_parts > 1 && p.f_part[f] < 0) shr.push_back(f);
-                else if (opts.n_parts == 1 || p.f_part[f] == opts.part) loc.push_back(f);
+                int f = q.level_fronts[k];
+                if (f == q.dense_root) continue;                    // factored by the dense-root kernels
+                if (opts.n_parts > 1 && q.f_part[f] < 0) shr.push_back(f);
+                else if (opts.n_parts == 1 || q.f_part[f] == opts.part) loc.push_back(f);
             }
             h->level_nlocal[l] = (int)loc.size();
+            h->level_nshared[l] = (int)shr.size();
             // fronts of other windows are dropped from the schedule: keep slots but never launch them
             int k = b;
             for (int f : loc) lf[k++] = f;
@@ -305,9 +317,9 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         }
         long long off = 0;
         for (int f : shared_list) {
-            long long Rf = 9LL * (p.f_np[f] + p.f_nb[f]) + 1;
+            long long Cf = 3LL * q.f_npad[f], ub = 3LL * q.f_nb[f] + 1, Rf = Cf + ub;
             h->h_shared_off[f] = off;
-            off += Rf * Rf + 9LL * p.f_np[f];
+            off += Rf * Cf + f3_ulen((int)ub) + Cf;
         }
         h->n_shared = (int)shared_list.size();
         h->shared_doubles = off + 4;      // + [lin loss, trial loss, quality, spare]
@@ -317,38 +329,48 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         AL(shared, (size_t)h->shared_doubles);
         cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
     }
-    AL(Lbuf, (size_t)p.L_doubles); AL(Ubuf, (size_t)p.U_doubles); AL(Linv, 81 * (size_t)N);
+    AL(Lbuf, (size_t)q.L_doubles); AL(Ubuf, (size_t)q.U_doubles); AL(Linv, (size_t)std::max(1LL, q.I_doubles));
     AL(st, 1); AL(d_prm, 1); AL(d_w, 4);
     cudaMemset(h->D.p, 0, sizeof(double) * 9 * (size_t)N);
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
 #undef AL
-    // shared-memory budgets
-    int dev = 0, max_optin = 0;
+    // shared-memory budgets and the kernel variant of every level
+    int dev = 0, max_optin = 0, n_sm = 148, smem_sm = 228 * 1024;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if (max_optin <= 0) max_optin = 227 * 1024;
-    h->max_smem_doubles = (max_optin - 1024) / 8;
-    cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
-    cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
-    cudaFuncSetAttribute(k_factor_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
-    h->level_smem_doubles.assign(p.n_levels, 96);
-    h->level_bs_bytes.assign(p.n_levels, 0);
-    h->level_fast.assign(p.n_levels, 1);
-    for (int f = 0; f < p.F; ++f) {
-        if (f == p.dense_root) continue;
-        int l = p.f_level[f];
-        long long Cf = 9LL * p.f_np[f], Rb = 9LL * p.f_nb[f], Rf = Cf + Rb + 1;
-        int nch = p.f_child_off[f + 1] - p.f_child_off[f];
-        long long meta = front_meta_doubles(p.f_np[f], p.f_np[f] + p.f_nb[f], nch);
-        long long need = ((Rf + 3) & ~3LL) * Cf + 192 + meta;
-        if (need > h->max_smem_doubles || meta == 0) h->level_fast[l] = 0;   // this level takes the generic kernel
-        if (need > h->max_smem_doubles) need = 96 + meta;        // panel stays in global memory
-        if (need > h->level_smem_doubles[l]) h->level_smem_doubles[l] = (int)need;
-        long long bs_min = (Rb + Cf + 16 + 81LL * p.f_np[f]) * 8, bs = bs_min + Rf * Cf * 8;
-        if (bs_min > max_optin - 1024) { delete h; return -5; }   // boundary too wide for the back-substitution kernel
-        if (bs > max_optin - 1024) bs = bs_min;                   // panel read straight from global memory
-        if (bs > h->level_bs_bytes[l]) h->level_bs_bytes[l] = (int)bs;
+    set_factor_smem<512, 1, true>(max_optin); set_factor_smem<512, 1, false>(max_optin);
+    set_factor_smem<256, 2, true>(max_optin); set_factor_smem<256, 2, false>(max_optin);
+    cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    h->level_variant.assign(q.n_levels, 0);
+    h->level_smem_bytes.assign(q.n_levels, 0);
+    h->level_bs_bytes.assign(q.n_levels, 0);
+    {
+        std::vector<long long> need_u(q.n_levels, 0), need_p(q.n_levels, 0), bs_min(q.n_levels, 0), bs_full(q.n_levels, 0);
+        std::vector<int> count(q.n_levels, 0);
+        for (int f = 0; f < q.F; ++f) {
+            if (f == q.dense_root) continue;
+            const int l = q.f_level[f];
+            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub;
+            need_u[l] = std::max(need_u[l], 8 * f3_smem_doubles(Rf, Cf, ub, true));
+            need_p[l] = std::max(need_p[l], 8 * f3_smem_doubles(Rf, Cf, ub, false));
+            bs_min[l] = std::max(bs_min[l], 8 * bs3_smem_doubles(Rf, Cf, false));
+            bs_full[l] = std::max(bs_full[l], 8 * bs3_smem_doubles(Rf, Cf, true));
+            if (opts.n_parts == 1 || q.f_part[f] < 0 || q.f_part[f] == opts.part) count[l]++;
+        }
+        for (int l = 0; l < q.n_levels; ++l) {
+            if (need_p[l] > max_optin || bs_min[l] > max_optin) { delete h; return -5; }   // front too wide for shared memory
+            int var = need_u[l] <= max_optin ? VAR_USMEM : 0;
+            long long need = var ? need_u[l] : need_p[l];
+            // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency)
+            if (count[l] > n_sm && 2 * (need + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
+            h->level_variant[l] = var;
+            h->level_smem_bytes[l] = (int)need;
+            h->level_bs_bytes[l] = (int)(bs_full[l] <= max_optin ? bs_full[l] : bs_min[l]);
+        }
     }
     // views
     ProblemView& pv = h->pv;
@@ -366,38 +388,24 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     av.node_eoff = h->d_node_eoff.p; av.node_edges = h->d_node_edges.p; av.pair_lo = h->d_pair_lo.p;
     av.pair_hi = h->d_pair_hi.p; av.pair_adj = h->d_pair_adj.p; av.pair_eoff = h->d_pair_eoff.p;
     av.pair_edges = h->d_pair_edges.p; av.P = p.P;
-    FrontMeta& fm = h->fm;
-    fm.np = h->d_np.p; fm.nb = h->d_nb.p; fm.nodes_off = h->d_nodes_off.p; fm.nodes = h->d_nodes.p;
-    fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.child_off = h->d_child_off.p; fm.children = h->d_children.p;
-    fm.cinv_off = h->d_cinv_off.p; fm.cinv = h->d_cinv.p; fm.hmap_off = h->d_hmap_off.p; fm.hmap = h->d_hmap.p;
+    Front3Meta& fm = h->fm;
+    fm.np = h->d_np.p; fm.npad = h->d_npad.p; fm.nb = h->d_nb.p; fm.vars_off = h->d_vars_off.p; fm.vars = h->d_vars.p;
+    fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.Ioff = h->d_Ioff.p; fm.child_off = h->d_child_off.p;
+    fm.children = h->d_children.p; fm.cmap_off = h->d_cmap_off.p; fm.cmap = h->d_cmap.p; fm.orig_off = h->d_orig_off.p;
+    fm.orig_rs = h->d_orig_rs.p; fm.orig_cs = h->d_orig_cs.p; fm.orig_src = h->d_orig_src.p;
     fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p; fm.mypart = opts.part;
     // dense root (loop-closure Schur complement)
-    if (p.dense_root >= 0) {
-        const int fr = p.dense_root, K = p.f_np[fr];
-        std::vector<int> rnodes(p.f_nodes.begin() + p.f_nodes_off[fr], p.f_nodes.begin() + p.f_nodes_off[fr] + K);
-        std::vector<int> pid, prow, pcol, ptr_, kids;
-        for (int i = 0; i < p.P; ++i) {
-            int a = p.root_slot[p.pair_lo[i]], b = p.root_slot[p.pair_hi[i]];
-            if (a < 0 || b < 0) continue;
-            // Ho[i] = H[lo dofs, hi dofs]; the block lands at (row slot > col slot)
-            if (a > b) { pid.push_back(i); prow.push_back(a); pcol.push_back(b); ptr_.push_back(0); }
-            else { pid.push_back(i); prow.push_back(b); pcol.push_back(a); ptr_.push_back(1); }
-        }
-        for (int k = p.f_child_off[fr]; k < p.f_child_off[fr + 1]; ++k) kids.push_back(p.f_children[k]);
-        cudaError_t e1 = h->d_root_nodes.upload(rnodes);
-        if (e1 == cudaSuccess) e1 = h->d_root_pid.upload(pid);
-        if (e1 == cudaSuccess) e1 = h->d_root_row.upload(prow);
-        if (e1 == cudaSuccess) e1 = h->d_root_col.upload(pcol);
-        if (e1 == cudaSuccess) e1 = h->d_root_tr.upload(ptr_);
+    if (q.dense_root >= 0) {
+        const int fr = q.dense_root, K = q.f_np[fr];
+        std::vector<int> rvars(q.f_vars.begin() + q.f_vars_off[fr], q.f_vars.begin() + q.f_vars_off[fr] + K), kids;
+        for (int k = q.f_child_off[fr]; k < q.f_child_off[fr + 1]; ++k) kids.push_back(k);
+        cudaError_t e1 = h->d_root_vars.upload(rvars);
         if (e1 == cudaSuccess) e1 = h->d_root_children.upload(kids);
-        if (e1 == cudaSuccess) e1 = h->d_root_slot.upload(p.root_slot);
-        if (e1 == cudaSuccess) e1 = h->root_x.alloc(9 * (size_t)K + 1);
+        if (e1 == cudaSuccess) e1 = h->root_x.alloc(3 * (size_t)K + 1);
         if (e1 != cudaSuccess) { delete h; return (int)e1; }
         RootView& rv = h->rv;
-        rv.R = h->Lbuf.p + p.f_Loff[fr]; rv.n = 9 * K; rv.ld = 9 * K + 1; rv.K = K;
-        rv.nodes = h->d_root_nodes.p; rv.pr_pid = h->d_root_pid.p; rv.pr_row = h->d_root_row.p; rv.pr_col = h->d_root_col.p;
-        rv.pr_tr = h->d_root_tr.p; rv.npairs = (int)pid.size(); rv.children = h->d_root_children.p;
-        rv.nchildren = (int)kids.size(); rv.root_slot = h->d_root_slot.p;
+        rv.R = h->Lbuf.p + q.f_Loff[fr]; rv.n = 3 * K; rv.ld = 3 * K + 1; rv.K = K; rv.front = fr;
+        rv.vars = h->d_root_vars.p; rv.children = h->d_root_children.p; rv.nchildren = (int)kids.size();
         h->has_root = true;
         cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128)));
         cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * DR_NB * DR_NB));
@@ -419,11 +427,12 @@ extern "C" void islam_pvgo_destroy(islam_pvgo* h) { delete h; }
 extern "C" int islam_pvgo_get_dims(const islam_pvgo* h, islam_pvgo_dims* d) {
     if (!h || !d) return -1;
     const Plan& p = h->plan;
+    const Plan3& q = h->p3;
     std::memset(d, 0, sizeof(*d));
-    d->N = p.N; d->E = p.E; d->M = p.M; d->P = p.P; d->F = p.F; d->levels = p.n_levels; d->band = p.band;
-    d->root_pivots = p.root_pivots; d->max_rows = p.max_rows; d->max_cols = p.max_cols;
-    d->n_shared_fronts = h->n_shared; d->L_doubles = p.L_doubles; d->U_doubles = p.U_doubles;
-    d->shared_doubles = h->shared_doubles; d->factor_flops = p.factor_flops;
+    d->N = p.N; d->E = p.E; d->M = p.M; d->P = p.P; d->F = q.F; d->levels = q.n_levels; d->band = p.band;
+    d->root_pivots = q.root_pivots; d->max_rows = q.max_rows; d->max_cols = q.max_cols;
+    d->n_shared_fronts = h->n_shared; d->L_doubles = q.L_doubles; d->U_doubles = q.U_doubles;
+    d->shared_doubles = h->shared_doubles; d->factor_flops = q.factor_flops;
     return 0;
 }
 
@@ -493,26 +502,30 @@ static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
 static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale);
 static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force);
 
-static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale, int which /*0 local, 2 shared*/) {
-    const Plan& p = h->plan;
+// `n` fronts of level l starting at d_level_fronts[first], in the given stage (solver3.cuh)
+static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int first, int n, double forced_scale, int stage) {
     const islam_lm_params& q = h->prm;
-    for (int l = 0; l < p.n_levels; ++l) {
-        int b = p.level_off[l];
-        int nloc = h->level_nlocal[l];
-        size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
-        if (which == 0 && nloc > 0) {
-            if (h->level_fast[l])
-                launch_pdl(k_factor_fast, nloc, F3_THREADS, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + b),
-                           h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p,
-                           h->Linv.p, (const double*)h->shared.p, q.lm_min, q.lm_max, forced_scale, 0, &h->st.p->chol_fail,
-                           (const islam_lm_params*)h->d_prm.p);
-            else
-                k_factor_level<<<nloc, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p,
-                                                              h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max,
-                                                              forced_scale, h->level_smem_doubles[l], 0, &h->st.p->chol_fail, h->d_prm.p);
-        }
+    const size_t smem = (size_t)h->level_smem_bytes[l];
+    const int var = h->level_variant[l];
+#define F3_LAUNCH(NT, MINB, US)                                                                                          \
+    launch_pdl(k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
+               h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \
+               h->shared.p, q.lm_min, q.lm_max, forced_scale, stage, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p)
+    switch (var) {
+        case VAR_USMEM | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, true);
+        case VAR_USMEM: return F3_LAUNCH(512, 1, true);
+        case VAR_SMALL_CTA: return F3_LAUNCH(256, 2, false);
+        default: return F3_LAUNCH(512, 1, false);
     }
-    if (which == 0) { int rc = launch_root_factor(h, s, forced_scale); if (rc) return rc; }
+#undef F3_LAUNCH
+}
+
+static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
+    const Plan3& p = h->p3;
+    for (int l = 0; l < p.n_levels; ++l)
+        if (h->level_nlocal[l] > 0) CK(launch_factor_level(h, s, l, p.level_off[l], h->level_nlocal[l], forced_scale, 0));
+    int rc = launch_root_factor(h, s, forced_scale);
+    if (rc) return rc;
     return (int)cudaGetLastError();
 }
 
@@ -523,8 +536,9 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
     const islam_lm_params& q = h->prm;
     const int force = forced_scale != 0.0;
     CK(cudaMemsetAsync(rv.R, 0, sizeof(double) * (size_t)rv.ld * rv.n, s));
-    int tasks = rv.K + rv.npairs;
-    k_root_orig<<<(tasks * 32 + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min, q.lm_max);
+    const Plan3& p = h->p3;
+    const int tasks = 9 * (p.f_orig_off[rv.front + 1] - p.f_orig_off[rv.front]) + rv.n;
+    k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min, q.lm_max);
     if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force);
     for (int k0 = 0; k0 < rv.n; k0 += DR_NB) {
         int nbk = std::min(DR_NB, rv.n - k0);
@@ -553,46 +567,25 @@ static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force) {
     return (int)cudaGetLastError();
 }
 
-// number of shared fronts scheduled at level l (they follow the local ones in d_level_fronts)
-static int level_nshared(const islam_pvgo* h, int l) {
-    if (h->opts.n_parts <= 1) return 0;
-    const Plan& p = h->plan;
-    int n = 0;
-    for (int k = p.level_off[l]; k < p.level_off[l + 1]; ++k)
-        if (p.f_part[p.level_fronts[k]] < 0) ++n;
-    return n;
-}
-
-static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_scale) {
-    const Plan& p = h->plan;
-    const islam_lm_params& q = h->prm;
-    for (int l = 0; l < p.n_levels; ++l) {
-        int ns = level_nshared(h, l);
-        if (!ns) continue;
-        int b = p.level_off[l] + h->level_nlocal[l];
-        size_t smem = sizeof(double) * (size_t)h->level_smem_doubles[l];
-        if (h->level_fast[l])
-            launch_pdl(k_factor_fast, ns, F3_THREADS, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + b), h->fm,
-                       (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p,
-                       (const double*)h->shared.p, q.lm_min, q.lm_max, forced_scale, 2, &h->st.p->chol_fail,
-                       (const islam_lm_params*)h->d_prm.p);
-        else
-            k_factor_level<<<ns, FAC_THREADS, smem, s>>>(h->st.p, h->d_level_fronts.p + b, h->fm, h->Hd.p, h->Ho.p, h->g.p,
-                                                        h->Lbuf.p, h->Ubuf.p, h->Linv.p, h->shared.p, q.lm_min, q.lm_max, forced_scale,
-                                                        h->level_smem_doubles[l], 2, &h->st.p->chol_fail, h->d_prm.p);
-    }
+// multi-GPU: the shared (separator) fronts, which follow the local ones in d_level_fronts.
+// stage 1 = partial frontal matrices into the all-reduce buffer, stage 2 = factorisation after the all-reduce
+static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_scale, int stage) {
+    const Plan3& p = h->p3;
+    for (int l = 0; l < p.n_levels; ++l)
+        if (h->level_nshared[l] > 0)
+            CK(launch_factor_level(h, s, l, p.level_off[l] + h->level_nlocal[l], h->level_nshared[l], forced_scale, stage));
     return (int)cudaGetLastError();
 }
 
 static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
-    const Plan& p = h->plan;
+    const Plan3& p = h->p3;
     { int rc = launch_root_solve(h, s, force); if (rc) return rc; }
     for (int l = p.n_levels - 1; l >= 0; --l) {
-        int n = h->level_nlocal[l] + level_nshared(h, l);
+        int n = h->level_nlocal[l] + h->level_nshared[l];
         if (!n) continue;
-        launch_pdl(k_backsolve_level, n, BS_THREADS2, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
-                   (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
-                   h->D.p, force, h->level_bs_bytes[l] / 8);
+        CK(launch_pdl(k_backsolve3, n, BS3_THREADS, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
+                      (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
+                      h->D.p, force, h->level_bs_bytes[l] / 8));
     }
     return (int)cudaGetLastError();
 }
@@ -635,7 +628,7 @@ extern "C" int islam_pvgo_solve(islam_pvgo* h, double diag_scale, double lm_min,
     islam_lm_params saved = h->prm;
     h->prm.lm_min = lm_min; h->prm.lm_max = lm_max;
     CK(cudaMemsetAsync(&h->st.p->chol_fail, 0, sizeof(int), s));
-    int rc = launch_factor(h, s, diag_scale, 0);
+    int rc = launch_factor(h, s, diag_scale);
     h->prm = saved;
     if (rc) return rc;
     rc = launch_backsolve(h, s, 1);
@@ -671,12 +664,9 @@ static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
     k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, np_, lin_sum_ptr(h), 1);
     k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
     if (h->opts.n_parts == 1) k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
-    rc = launch_factor(h, s, 0.0, 0);
+    rc = launch_factor(h, s, 0.0);
     if (rc) return rc;
-    if (h->opts.n_parts > 1 && h->n_shared > 0) {
-        k_shared_base<<<h->n_shared, FAC_THREADS, 0, s>>>(h->st.p, h->d_shared_fronts.p, h->fm, h->Hd.p, h->Ho.p, h->g.p,
-                                                          h->Ubuf.p, h->shared.p);
-    }
+    if (h->opts.n_parts > 1 && h->n_shared > 0) return launch_factor_shared(h, s, 0.0, 1);
     return (int)cudaGetLastError();
 }
 
@@ -687,7 +677,7 @@ static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
     int rc = 0;
     if (h->opts.n_parts > 1) {
         k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
-        rc = launch_factor_shared(h, s, 0.0);
+        rc = launch_factor_shared(h, s, 0.0, 2);
         if (rc) return rc;
     }
     rc = launch_backsolve(h, s, 0);
@@ -725,7 +715,7 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
     k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
     k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
     CK(cudaEventRecord(ev[1], s));
-    if (!rc) rc = launch_factor(h, s, 0.0, 0);
+    if (!rc) rc = launch_factor(h, s, 0.0);
     CK(cudaEventRecord(ev[2], s));
     if (!rc) rc = launch_backsolve(h, s, 0);
     CK(cudaEventRecord(ev[3], s));
@@ -784,11 +774,11 @@ extern "C" int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* 
     *n = 2;
     return 0;
 }
-// owner window of every pose: >= 0 private to that rank, -1 shared (solved redundantly on every rank)
-extern "C" int islam_pvgo_node_parts(const islam_pvgo* h, int32_t* out_host) {
+// owner window of every 3-dof variable (3N: tau, phi, v per pose): >= 0 private to that rank, -1 shared
+extern "C" int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host) {
     if (!h || !out_host) return -1;
-    const Plan& p = h->plan;
-    for (int n = 0; n < p.N; ++n) out_host[n] = p.f_part[p.node_front[n]];
+    const Plan3& p = h->p3;
+    for (int v = 0; v < p.V; ++v) out_host[v] = p.f_part[p.var_front[v]];
     return 0;
 }
 
@@ -889,7 +879,7 @@ extern "C" int islam_pvgo_align(islam_pvgo* h, const float* target, float* nout,
 }
 
 // ---- host-only introspection of the symbolic plan (no GPU needed; used by the CPU test-suite) -------------------------
-struct islam_plan { Plan plan; };
+struct islam_plan { Plan plan; Plan3 plan3; };
 
 extern "C" int islam_plan_build(islam_plan** out, int32_t N, int32_t E, const int64_t* links, const islam_pvgo_opts* o) {
     if (!out) return -1;
@@ -903,6 +893,7 @@ extern "C" int islam_plan_build(islam_plan** out, int32_t N, int32_t E, const in
     islam_plan* pl = new (std::nothrow) islam_plan();
     if (!pl) return -1;
     int rc = build_plan(N, E, links, so, pl->plan);
+    if (!rc) rc = build_plan3(pl->plan, links, so, pl->plan3);
     if (rc) { delete pl; return rc; }
     *out = pl;
     return 0;
@@ -914,12 +905,15 @@ extern "C" int64_t islam_plan_array(const islam_plan* pl, const char* name, cons
 #define ARR(nm, vec) if (!std::strcmp(name, nm)) { *ptr = (vec).data(); return (int64_t)(vec).size(); }
     ARR("pair_lo", p.pair_lo) ARR("pair_hi", p.pair_hi) ARR("pair_adj", p.pair_adj) ARR("pair_eoff", p.pair_eoff)
     ARR("pair_edges", p.pair_edges) ARR("node_eoff", p.node_eoff) ARR("node_edges", p.node_edges)
-    ARR("edge_pair", p.edge_pair) ARR("f_np", p.f_np) ARR("f_nb", p.f_nb) ARR("f_nodes_off", p.f_nodes_off)
-    ARR("f_nodes", p.f_nodes) ARR("f_Loff", p.f_Loff) ARR("f_Uoff", p.f_Uoff) ARR("f_parent", p.f_parent)
-    ARR("f_level", p.f_level) ARR("f_part", p.f_part) ARR("f_child_off", p.f_child_off) ARR("f_children", p.f_children)
-    ARR("c_inv_off", p.c_inv_off) ARR("c_inv", p.c_inv) ARR("f_hmap_off", p.f_hmap_off) ARR("hmap", p.hmap)
-    ARR("level_off", p.level_off) ARR("level_fronts", p.level_fronts) ARR("node_front", p.node_front)
-    ARR("node_slot", p.node_slot) ARR("node_pos", p.node_pos)
+    ARR("edge_pair", p.edge_pair)
+    const Plan3& q = pl->plan3;
+    ARR("v3_np", q.f_np) ARR("v3_npad", q.f_npad) ARR("v3_nb", q.f_nb) ARR("v3_vars_off", q.f_vars_off) ARR("v3_vars", q.f_vars)
+    ARR("v3_Loff", q.f_Loff) ARR("v3_Uoff", q.f_Uoff) ARR("v3_Ioff", q.f_Ioff) ARR("v3_parent", q.f_parent)
+    ARR("v3_level", q.f_level) ARR("v3_part", q.f_part) ARR("v3_child_off", q.f_child_off) ARR("v3_children", q.f_children)
+    ARR("v3_cmap_off", q.c_map_off) ARR("v3_cmap", q.c_map) ARR("v3_orig_off", q.f_orig_off) ARR("v3_orig_rs", q.orig_rs)
+    ARR("v3_orig_cs", q.orig_cs) ARR("v3_orig_src", q.orig_src) ARR("v3_level_off", q.level_off)
+    ARR("v3_level_fronts", q.level_fronts) ARR("v3_var_front", q.var_front) ARR("v3_var_slot", q.var_slot)
+    ARR("v3_var_pos", q.var_pos) ARR("v3_root_slot", q.root_slot) ARR("v3_scalars", q.scalars)
 #undef ARR
     return -1;
 }

@@ -43,11 +43,14 @@ class ShardedPVGO:
         self.shared = _wrap(p.value, n.value, self.s.device)
         _lib.check(L.islam_pvgo_sums_buffer(h, C.byref(p), C.byref(n)), 'islam_pvgo_sums_buffer')
         self.sums = _wrap(p.value, n.value, self.s.device)
-        parts = np.zeros(N, np.int32)
-        _lib.check(L.islam_pvgo_node_parts(h, parts.ctypes.data), 'islam_pvgo_node_parts')
-        self.node_parts = parts
-        mine = (parts == self.rank) | ((parts < 0) & (self.rank == 0))
-        self._mine = torch.as_tensor(mine, device=self.s.device)
+        parts = np.zeros(3 * N, np.int32)
+        _lib.check(L.islam_pvgo_var_parts(h, parts.ctypes.data), 'islam_pvgo_var_parts')
+        self.var_parts = parts = parts.reshape(N, 3)            # [tau, phi, v] of every pose
+        # a pose / velocity is reported by the rank that solves it: the owner of a private variable, else rank 0
+        pose_owner = np.where((parts[:, :2] >= 0).any(1), parts[:, :2].max(1), 0)
+        vel_owner = np.where(parts[:, 2] >= 0, parts[:, 2], 0)
+        self._mine_pose = torch.as_tensor(pose_owner == self.rank, device=self.s.device)
+        self._mine_vel = torch.as_tensor(vel_owner == self.rank, device=self.s.device)
         self._nccl = dist.get_backend(group) == 'nccl'
 
     # passthroughs
@@ -96,9 +99,8 @@ class ShardedPVGO:
     def get_state(self):
         """Each pose is taken from the rank that solves it (shared poses from rank 0) and summed across ranks."""
         n, v = self.s.get_state()
-        m = self._mine.unsqueeze(-1)
-        n = torch.where(m, n, torch.zeros_like(n))
-        v = torch.where(m, v, torch.zeros_like(v))
+        n = torch.where(self._mine_pose.unsqueeze(-1), n, torch.zeros_like(n))
+        v = torch.where(self._mine_vel.unsqueeze(-1), v, torch.zeros_like(v))
         self._allreduce(n)
         self._allreduce(v)
         return n, v

@@ -61,9 +61,9 @@ def _worker(rank, world, port, name, out_dir):
         dist.all_reduce(t)
         return t.numpy()
     D = mf_emul.solve_sharded(plan, rank, Hd, Ho, gg, 1.0 + 1e-4, allreduce)
-    node_part = plan['f_part'][plan['node_front']]
-    mine = (node_part == rank) | ((node_part < 0) & (rank == 0))
-    t = torch.from_numpy(np.where(mine[:, None], D, 0.0))
+    var_part = plan['part'][plan['var_front']]               # every variable is reported by the rank that solves it
+    mine = (var_part == rank) | ((var_part < 0) & (rank == 0))
+    t = torch.from_numpy(np.where(mine[:, None], D.reshape(-1, 3), 0.0).reshape(-1, 9))
     dist.all_reduce(t)                                           # ShardedPVGO.get_state's gather
     Hs = torch.from_numpy(H.copy()); gs = torch.from_numpy(gg.copy())
     dist.all_reduce(Hs); dist.all_reduce(gs)

@@ -13,6 +13,7 @@ CASES = {
     'band3_odd': lambda: synth.config2(N=57, band=3),
     'chain': lambda: synth.config3(N=131),
     'loop_closures': lambda: synth.config4(N=400, n_lc=6, min_gap=50),
+    'dense_root': lambda: synth.config4(N=500, n_lc=40, min_gap=60),
     'window9': lambda: synth.window(),
     'two_nodes': lambda: synth.window(N=2),
 }
@@ -26,12 +27,14 @@ def test_plan_solves_like_dense(name, opts):
     H, gg, _, _ = lm.assemble(lm._res())
     H = H.toarray()
     plan = mf_emul.get_plan(g.N, g.links, **opts)
-    # every pose is a pivot exactly once; parents come later; levels respect the tree
-    assert sorted(np.concatenate([plan['f_nodes'][plan['f_nodes_off'][f]:plan['f_nodes_off'][f] + plan['f_np'][f]]
-                                  for f in range(len(plan['f_np']))]).tolist()) == list(range(g.N))
-    par = plan['f_parent']
+    # every 3-dof variable (tau, phi, v of every pose) is a pivot exactly once; parents come later; levels respect the tree
+    piv = np.concatenate([plan['vars'][plan['vars_off'][f]:plan['vars_off'][f] + plan['np'][f]] for f in range(plan['F'])])
+    assert sorted(piv.tolist()) == list(range(3 * g.N))
+    sparse = np.arange(plan['F']) != plan['dense_root']          # the dense root is not padded to whole 9-column steps
+    assert np.all(plan['npad'][sparse] % 3 == 0) and np.all(plan['npad'] >= plan['np']) and np.all(plan['npad'] - plan['np'] < 3)
+    par = plan['parent']
     assert all(p == -1 or p > f for f, p in enumerate(par))
-    assert all(p == -1 or plan['f_level'][p] > plan['f_level'][f] for f, p in enumerate(par))
+    assert all(p == -1 or plan['level'][p] > plan['level'][f] for f, p in enumerate(par))
     Hd, Ho = mf_emul.blocks_from_dense(H, plan, g.N)
     scale = 1.0 + 1e-4
     D = mf_emul.solve(plan, Hd, Ho, gg, scale)
@@ -42,27 +45,43 @@ def test_plan_solves_like_dense(name, opts):
     assert np.abs(D - Dref).max() <= 1e-9 * np.abs(Dref).max()
 
 
+def test_separators_are_trimmed_to_one_velocity():
+    """The point of the variable-level ordering: a separator of the band-b chain holds tau/phi of b poses but ONE velocity."""
+    g = synth.config2(N=600, band=8)
+    plan = mf_emul.get_plan(g.N, g.links)
+    top = int(np.argmax(plan['level']))                         # the root separator
+    vs = plan['vars'][plan['vars_off'][top]:plan['vars_off'][top] + plan['np'][top]]
+    assert len(vs) == 2 * 8 + 1 and np.sum(vs % 3 == 2) == 1
+    assert len(np.unique(vs[vs % 3 != 2] // 3)) == 8
+    assert plan['max_cols'] <= 72 and plan['n_levels'] <= 8
+
+
 def test_multi_window_partition_is_consistent():
     g = synth.config2(N=600, band=8)
     plan = mf_emul.get_plan(g.N, g.links, n_parts=4)
-    part = plan['f_part']
+    part = plan['part']
     assert set(part.tolist()) == {-1, 0, 1, 2, 3}
-    # private fronts only see poses of their own window or shared poses
-    node_part = part[plan['node_front']]
+    # private fronts only see variables of their own window or shared variables
+    var_part = part[plan['var_front']]
     for f in range(len(part)):
         if part[f] < 0:
             continue
-        nodes = plan['f_nodes'][plan['f_nodes_off'][f]:plan['f_nodes_off'][f + 1]]
-        assert set(node_part[nodes].tolist()) <= {-1, int(part[f])}
+        vs = plan['vars'][plan['vars_off'][f]:plan['vars_off'][f + 1]]
+        assert set(var_part[vs[vs >= 0]].tolist()) <= {-1, int(part[f])}
     # shared fronts' ancestors are shared
-    for f, p in enumerate(plan['f_parent']):
+    for f, p in enumerate(plan['parent']):
         if part[f] < 0 and p >= 0:
             assert part[p] < 0
     # windows are contiguous index ranges
     for w in range(4):
-        idx = np.where(node_part == w)[0]
-        shared_between = node_part[idx.min():idx.max() + 1]
-        assert set(shared_between.tolist()) <= {w, -1}
+        idx = np.where(var_part == w)[0]
+        assert set(var_part[idx.min():idx.max() + 1].tolist()) <= {w, -1}
+    # every factor touches private variables of at most one window (ownership rule of islam_pvgo_create)
+    vp, eo, po_ = mf_emul.owners(plan, g.links)
+    for (i, j), o in zip(g.links, eo):
+        assert set(np.concatenate([vp[i, :2], vp[j, :2]]).tolist()) <= {-1, int(o)}
+    for i, o in enumerate(po_):
+        assert set(np.concatenate([vp[i], vp[i + 1]]).tolist()) <= {-1, int(o)}
 
 
 def test_invalid_graphs_are_rejected():

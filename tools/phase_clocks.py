@@ -1,4 +1,5 @@
-"""Developer probe: per-phase clock64() stamps of k_factor_fast (block 0) from a -DISLAM_PHASE_CLOCKS build."""
+"""Developer probe: per-phase clock64() stamps of k_factor3 (block 0 of the level whose grid size is argv[1]) from a
+-DISLAM_PHASE_CLOCKS build (`python -m islam_b200.build --phase-clocks`)."""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from islam_b200 import _lib
@@ -12,20 +13,21 @@ s.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.los
 s.set_state(g.init_nodes, g.init_vels)
 s.linearize()
 L = C.CDLL(_lib.LIB_PATH)
-L.islam_debug_phase_grid(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
-for _ in range(3):
-    s.solve(1.0001)
-buf = (C.c_longlong * 64)()
-L.islam_debug_phase_clocks(buf)
-c = np.array(buf[:], dtype=np.int64)
-print('level with grid', sys.argv[1:] , 'block 0:')
-names = {0: 'start', 1: 'staged', 2: 'assembled', 3: 'panel done', 4: 'L written', 5: 'U done'}
-t0 = c[0]
-for k in (0, 1, 2):
-    print(names[k], c[k] - t0)
-for jb in range(8):
-    print('jb', jb, 'chol', c[10 + 3 * jb] - t0, 'trsm', c[11 + 3 * jb] - t0, 'update', c[12 + 3 * jb] - t0)
-for k in (3, 4, 5):
-    print(names[k], c[k] - t0)
-
-print('A iter0: issue done', c[41]-c[40], 'sum+store done', c[42]-c[40], 'iter1 start', c[43]-c[40])
+for grid in [int(a) for a in sys.argv[1:]] or [1]:
+    L.islam_debug_phase_grid(grid)
+    for _ in range(3):
+        s.solve(1.0001)
+    buf = (C.c_longlong * 64)()
+    L.islam_debug_phase_clocks(buf)
+    c = np.array(buf[:], dtype=np.int64)
+    print('level with grid', grid, 'block 0:')
+    names = {0: 'start', 1: 'zeroed + previous level done', 2: 'original entries', 3: 'children added', 4: 'panel done',
+             5: 'L written', 6: 'U done'}
+    t0 = c[0]
+    for k in (0, 1, 2, 3):
+        print(' ', names[k], c[k] - t0)
+    for jb in range(8):
+        if c[10 + 3 * jb] > t0:
+            print('  jb', jb, 'start', c[10 + 3 * jb] - t0, 'trsm', c[11 + 3 * jb] - t0, 'update', c[12 + 3 * jb] - t0)
+    for k in (4, 5, 6):
+        print(' ', names[k], c[k] - t0)
