@@ -27,6 +27,7 @@ struct Front3Meta {
     const int* orig_rs;     // row slot
     const int* orig_cs;     // column slot (a pivot)
     const int* orig_src;    // (offset << 2) | (2: Ho, 0: Hd) | (1: transposed)
+    const unsigned short* dmap;   // per element of every child's packed U: destination in the parent's shared memory | nullptr
     const int* part;        // [F] owning window or -1 (shared)
     const long long* shared_off;  // [F] offset into the shared all-reduce buffer or -1
     int mypart;                   // this rank's window (multi-GPU)

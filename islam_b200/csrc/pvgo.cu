@@ -171,6 +171,7 @@ struct islam_pvgo {
         d_orig_cs, d_orig_src, d_part, d_level_fronts, d_shared_fronts, d_root_vars, d_root_children;
     DevBuf<long long> d_Loff, d_Uoff, d_Ioff, d_shared_off;
     DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
+    DevBuf<unsigned short> d_dmap;
     RootView rv;
     bool has_root = false;
     DevBuf<LMState> st;
@@ -178,7 +179,7 @@ struct islam_pvgo {
     DevBuf<double> d_w;
     LMState* st_host = nullptr;     // pinned mirror
     int nblk_vo = 0, nblk_imu = 0;
-    // per level: kernel variant (bit 0: update matrix in shared memory, bit 1: 256-thread CTAs, two per SM),
+    // per level: kernel variant (solver3.cuh MODE | VAR_SMALL_CTA: 256-thread CTAs, two per SM),
     // dynamic shared memory of the factor / back-substitution kernels
     std::vector<int> level_variant, level_smem_bytes, level_bs_bytes;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
@@ -202,7 +203,7 @@ struct islam_pvgo {
         for (auto* b : fb) b->release();
         DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x};
         for (auto* b : db) b->release();
-        d_Loff.release(); d_Uoff.release(); d_Ioff.release(); d_shared_off.release();
+        d_Loff.release(); d_Uoff.release(); d_Ioff.release(); d_shared_off.release(); d_dmap.release();
         st.release(); d_prm.release(); d_w.release();
     }
 };
@@ -218,11 +219,11 @@ extern "C" void islam_lm_default_params(islam_lm_params* p) {
     p->max_steps = 10; p->patience = 3; p->use_scheduler = 1; p->decreasing = 1e-3;   // pvgo.py:172
 }
 
-// kernel variants of one level (see islam_pvgo::level_variant)
-enum { VAR_USMEM = 1, VAR_SMALL_CTA = 2 };
+// kernel variant of one level (islam_pvgo::level_variant): solver3.cuh MODE in bits 0-1 | VAR_SMALL_CTA
+enum { VAR_SMALL_CTA = 4 };
 
-template <int NT, int MINB, bool U_SMEM> static void set_factor_smem(int bytes) {
-    cudaFuncSetAttribute(k_factor3<NT, MINB, U_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+template <int NT, int MINB, int MODE> static void set_factor_smem(int bytes) {
+    cudaFuncSetAttribute(k_factor3<NT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const int64_t* links, const islam_pvgo_opts* o) {
@@ -342,35 +343,60 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if (max_optin <= 0) max_optin = 227 * 1024;
-    set_factor_smem<512, 1, true>(max_optin); set_factor_smem<512, 1, false>(max_optin);
-    set_factor_smem<256, 2, true>(max_optin); set_factor_smem<256, 2, false>(max_optin);
+    set_factor_smem<512, 1, 2>(max_optin); set_factor_smem<512, 1, 1>(max_optin); set_factor_smem<512, 1, 0>(max_optin);
+    set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin);
     cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     h->level_variant.assign(q.n_levels, 0);
     h->level_smem_bytes.assign(q.n_levels, 0);
     h->level_bs_bytes.assign(q.n_levels, 0);
     {
-        std::vector<long long> need_u(q.n_levels, 0), need_p(q.n_levels, 0), bs_min(q.n_levels, 0), bs_full(q.n_levels, 0);
+        std::vector<long long> need[3], bs_min(q.n_levels, 0), bs_full(q.n_levels, 0);
+        for (auto& v : need) v.assign(q.n_levels, 0);
         std::vector<int> count(q.n_levels, 0);
         for (int f = 0; f < q.F; ++f) {
             if (f == q.dense_root) continue;
             const int l = q.f_level[f];
             const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub;
-            need_u[l] = std::max(need_u[l], 8 * f3_smem_doubles(Rf, Cf, ub, true));
-            need_p[l] = std::max(need_p[l], 8 * f3_smem_doubles(Rf, Cf, ub, false));
+            for (int mode = 0; mode < 3; ++mode) need[mode][l] = std::max(need[mode][l], 8 * f3_smem_doubles(Rf, Cf, ub, mode));
             bs_min[l] = std::max(bs_min[l], 8 * bs3_smem_doubles(Rf, Cf, false));
             bs_full[l] = std::max(bs_full[l], 8 * bs3_smem_doubles(Rf, Cf, true));
             if (opts.n_parts == 1 || q.f_part[f] < 0 || q.f_part[f] == opts.part) count[l]++;
         }
         for (int l = 0; l < q.n_levels; ++l) {
-            if (need_p[l] > max_optin || bs_min[l] > max_optin) { delete h; return -5; }   // front too wide for shared memory
-            int var = need_u[l] <= max_optin ? VAR_USMEM : 0;
-            long long need = var ? need_u[l] : need_p[l];
+            if (bs_min[l] > max_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
+            int var = need[2][l] <= max_optin ? 2 : (need[1][l] <= max_optin ? 1 : 0);
+            const long long bytes = need[var][l];
             // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency)
-            if (count[l] > n_sm && 2 * (need + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
+            if (var > 0 && count[l] > n_sm && 2 * (bytes + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
             h->level_variant[l] = var;
-            h->level_smem_bytes[l] = (int)need;
+            h->level_smem_bytes[l] = (int)bytes;
             h->level_bs_bytes[l] = (int)(bs_full[l] <= max_optin ? bs_full[l] : bs_min[l]);
         }
+    }
+    // extend-add destination maps (solver3.cuh A2) for the parents whose whole frontal matrix sits in shared memory
+    h->fm.dmap = nullptr;
+    if (q.U_doubles <= (1LL << 27)) {                           // (a 2-byte entry per element of every update matrix)
+        std::vector<unsigned short> dmap((size_t)q.U_doubles, 0xFFFF);
+        for (int f = 0; f < q.F; ++f) {
+            if (f == q.dense_root || (h->level_variant[q.f_level[f]] & 3) != 2) continue;
+            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub, ld = f3_ld(Rf), uoff = ld * Cf + 4;
+            for (int k = q.f_child_off[f]; k < q.f_child_off[f + 1]; ++k) {
+                const int c = q.f_children[k], ubc = 3 * q.f_nb[c] + 1;
+                const int* cm = &q.c_map[q.c_map_off[k]];
+                unsigned short* dm = dmap.data() + q.f_Uoff[c];
+                for (int cc = 0; cc < ubc - 1; ++cc) {
+                    const int pc = 3 * cm[cc / 3] + cc % 3;
+                    for (int r = cc; r < ubc; ++r) {
+                        const int pr = (r == ubc - 1) ? Rf - 1 : 3 * cm[r / 3] + r % 3;
+                        const int dst = pc < Cf ? pr + pc * ld : uoff + f3_uidx(pr - Cf, pc - Cf, ub);
+                        dm[f3_uidx(r, cc, ubc)] = (unsigned short)dst;       // < 29 k doubles of shared memory
+                    }
+                }
+            }
+        }
+        cudaError_t e1 = h->d_dmap.upload(dmap);
+        if (e1 != cudaSuccess) { delete h; return (int)e1; }
+        h->fm.dmap = h->d_dmap.p;
     }
     // views
     ProblemView& pv = h->pv;
@@ -430,7 +456,7 @@ extern "C" int islam_pvgo_get_dims(const islam_pvgo* h, islam_pvgo_dims* d) {
     const Plan3& q = h->p3;
     std::memset(d, 0, sizeof(*d));
     d->N = p.N; d->E = p.E; d->M = p.M; d->P = p.P; d->F = q.F; d->levels = q.n_levels; d->band = p.band;
-    d->root_pivots = q.root_pivots; d->max_rows = q.max_rows; d->max_cols = q.max_cols;
+    d->root_pivots = q.root_pivots / 2; d->max_rows = q.max_rows; d->max_cols = q.max_cols;
     d->n_shared_fronts = h->n_shared; d->L_doubles = q.L_doubles; d->U_doubles = q.U_doubles;
     d->shared_doubles = h->shared_doubles; d->factor_flops = q.factor_flops;
     return 0;
@@ -512,10 +538,11 @@ static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int
                h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \
                h->shared.p, q.lm_min, q.lm_max, forced_scale, stage, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p)
     switch (var) {
-        case VAR_USMEM | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, true);
-        case VAR_USMEM: return F3_LAUNCH(512, 1, true);
-        case VAR_SMALL_CTA: return F3_LAUNCH(256, 2, false);
-        default: return F3_LAUNCH(512, 1, false);
+        case 2 | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, 2);
+        case 2: return F3_LAUNCH(512, 1, 2);
+        case 1 | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, 1);
+        case 1: return F3_LAUNCH(512, 1, 1);
+        default: return F3_LAUNCH(512, 1, 0);
     }
 #undef F3_LAUNCH
 }

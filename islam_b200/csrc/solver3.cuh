@@ -26,48 +26,17 @@ __device__ int g_phase_grid = 1;
 #define PHASE(n) do { } while (0)
 #endif
 
-constexpr int F3_HEAD = 192;     // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1 diagonal)
+constexpr int F3_HEAD = 192 + 128;   // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
+                                      // diagonal), then 256 ints of staged child maps
+constexpr int F3_CMAP_INTS = 256;
+constexpr int F3_PRE = 8;            // original entries per thread whose maps are resolved before the grid dependency
 
 __host__ __device__ __forceinline__ int f3_ld(int Rf) { return (Rf + 3) & ~3; }      // 32-byte aligned columns
 __host__ __device__ __forceinline__ long long f3_ulen(int ub) { return (long long)ub * (ub + 1) / 2; }
 // packed lower triangle, column-major: element (r, c), r >= c
 __host__ __device__ __forceinline__ int f3_uidx(int r, int c, int ub) { return c * ub - c * (c - 1) / 2 + (r - c); }
-__host__ __device__ __forceinline__ long long f3_smem_doubles(int Rf, int Cf, int ub, bool u_smem) {
-    return F3_HEAD + (long long)f3_ld(Rf) * Cf + 4 + (u_smem ? f3_ulen(ub) : 0);
-}
-
-// right-looking 9x9 Cholesky in registers (packed lower A -> L), reciprocal diagonal in linv
-__device__ __forceinline__ bool chol9_rl(double* A, double* linv) {
-    bool ok = true;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-        double d = A[c * (c + 1) / 2 + c];
-        if (!(d > 0.0) || !(d < 1e300)) { ok = false; d = 1.0; }
-        double inv = rsqrt(d);
-        inv = inv * (1.5 - 0.5 * d * inv * inv);             // one Newton step: full double accuracy
-        linv[c] = inv;
-        A[c * (c + 1) / 2 + c] = d * inv;
-#pragma unroll
-        for (int r = c + 1; r < 9; ++r) A[r * (r + 1) / 2 + c] *= inv;
-#pragma unroll
-        for (int r = c + 1; r < 9; ++r)
-#pragma unroll
-            for (int c2 = c + 1; c2 <= r; ++c2) A[r * (r + 1) / 2 + c2] -= A[r * (r + 1) / 2 + c] * A[c2 * (c2 + 1) / 2 + c];
-    }
-    return ok;
-}
-
-// column `col` (< 9) of the inverse of the packed lower-triangular L, branch-free: entries above the diagonal
-// come out as exact zeros because the partial sums only ever see zeros there
-__device__ __forceinline__ void tri_inv_col_uniform(const double* L, const double* linv, int col, double* x) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) s += L[i * (i + 1) / 2 + k] * x[k];
-        x[i] = (i == col) ? linv[i] : -s * linv[i];
-        if (i < col) x[i] = 0.0;
-    }
+__host__ __device__ __forceinline__ long long f3_smem_doubles(int Rf, int Cf, int ub, int mode) {
+    return F3_HEAD + (mode >= 1 ? (long long)f3_ld(Rf) * Cf + 4 : 0) + (mode == 2 ? f3_ulen(ub) : 0);
 }
 
 // ---- numeric factorisation of one level ------------------------------------------------------------------------------
@@ -78,7 +47,9 @@ __device__ __forceinline__ void tri_inv_col_uniform(const double* L, const doubl
 // Per shared front the buffer holds [P compact (Rf x Cf)] [U packed] [original pivot diagonal (Cf)]: PyPose's clamp_ acts
 // on the fully summed diagonal of J^T W J before damping (A.4), so the diagonal travels separately.
 // Linv: per 9-column block step the inverse of its 9x9 diagonal Cholesky block (row-major), for the back-substitution.
-template <int NT, int MINB, bool U_SMEM>
+// MODE 2: panel and update matrix in shared memory; 1: panel in shared memory, update matrix accumulated in global memory;
+// 0: both in global memory (boundary too wide for shared memory: chain separators that see a big loop-closure root).
+template <int NT, int MINB, int MODE>
 __global__ void __launch_bounds__(NT, MINB)
 k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3Meta m,
           const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
@@ -87,6 +58,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
           int* chol_fail, const islam_lm_params* __restrict__ prm) {
     // Launched with programmatic stream serialisation (PDL): everything up to cudaGridDependencySynchronize() only
     // touches the immutable symbolic plan and this CTA's shared memory, so it overlaps the tail of the previous level.
+    constexpr bool P_SMEM = MODE >= 1, U_SMEM = MODE == 2;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
@@ -95,42 +67,77 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     double* sLinv = smem;                      // 2 x 81 (+ pad): double-buffered inverse diagonal blocks
     const int np = m.np[f], npad = m.npad[f], nb = m.nb[f];
     const int Cf = 3 * npad, Rb = 3 * nb, Rf = Cf + Rb + 1, ub = Rb + 1, nbs = npad / 3;
-    const int ld = f3_ld(Rf);
+    const int ld = P_SMEM ? f3_ld(Rf) : Rf;
     const int ulen = (int)f3_ulen(ub);
-    double* P = smem + F3_HEAD;
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
+    double* P = P_SMEM ? smem + F3_HEAD : Lg;
     double* Uw = U_SMEM ? P + ld * Cf + 4 : Ug;
     const int* vars = m.vars + m.vars_off[f];
     const int k0 = m.child_off[f], nch = m.child_off[f + 1] - k0;
-    for (int i = tid; i < ld * Cf + 4; i += NT) P[i] = 0.0;
+    const int o0 = m.orig_off[f], no = m.orig_off[f + 1] - o0;
+    if (P_SMEM)
+        for (int i = tid; i < ld * Cf + 4; i += NT) P[i] = 0.0;
     if (U_SMEM)
         for (int i = tid; i < ulen; i += NT) Uw[i] = 0.0;
+    // resolve this thread's first F3_PRE original entries (immutable maps -> source offset, destination) and stage the
+    // children's boundary -> slot maps, all before the grid dependency: only the value loads remain afterwards
+    int osrc[F3_PRE], odst[F3_PRE];
+    auto resolve = [&](int idx, int& src_off, int& dst) {
+        const int e = idx / 9, k = idx - 9 * e, c = k / 3, r = k - 3 * c;
+        const int rs = m.orig_rs[o0 + e], cs = m.orig_cs[o0 + e], src = m.orig_src[o0 + e];
+        dst = -1;
+        src_off = 0;
+        if (rs == cs && r < c) return;                                 // diagonal block: lower triangle only
+        src_off = (((src >> 2) + ((src & 1) ? 9 * c + r : 9 * r + c)) << 1) | ((src >> 1) & 1);   // bit 0: Ho
+        dst = (3 * rs + r) + (3 * cs + c) * ld;
+        if (rs == cs && r == c) dst |= 0x40000000;                     // a pivot diagonal entry
+    };
+#pragma unroll
+    for (int u = 0; u < F3_PRE; ++u) {
+        odst[u] = -1; osrc[u] = 0;
+        if (stage != 2 && tid + u * NT < 9 * no) resolve(tid + u * NT, osrc[u], odst[u]);
+    }
+    int* scm = reinterpret_cast<int*>(smem + 192);
+    int cm_total = 0;
+    for (int k = 0; k < nch; ++k) cm_total += m.nb[m.children[k0 + k]];
+    const bool cm_staged = cm_total <= F3_CMAP_INTS;
+    if (cm_staged)
+        for (int i = tid; i < cm_total; i += NT) scm[i] = m.cmap[m.cmap_off[k0] + i];       // children's maps are contiguous
     cudaGridDependencySynchronize();           // previous level (children's U, LM state) complete and visible
     cudaTriggerProgrammaticLaunchCompletion(); // the next level may start its preamble
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
     const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
-    const bool u_accumulates = U_SMEM || nch > 0 || stage != 0;
-    if (!U_SMEM && u_accumulates)
+    if (!P_SMEM)
+        for (int i = tid; i < Rf * Cf; i += NT) P[i] = 0.0;
+    if (!U_SMEM)                               // the update matrix accumulates in place in global memory
         for (int i = tid; i < ulen; i += NT) Ug[i] = 0.0;
     __syncthreads();
     PHASE(1);
 
     // A1. original entries of J^T W J / -J^T W r first touched by this front (disjoint destinations)
     if (stage != 2) {
-        const int o0 = m.orig_off[f], no = m.orig_off[f + 1] - o0;
-        for (int idx = tid; idx < 9 * no; idx += NT) {
-            const int e = idx / 9, k = idx - 9 * e, c = k / 3, r = k - 3 * c;
-            const int rs = m.orig_rs[o0 + e], cs = m.orig_cs[o0 + e], src = m.orig_src[o0 + e];
-            if (rs == cs && r < c) continue;                       // diagonal block: lower triangle only
-            const double* arr = (src & 2) ? Ho : Hd;
-            double v = arr[(size_t)(src >> 2) + ((src & 1) ? 9 * c + r : 9 * r + c)];
-            if (rs == cs && r == c) {
-                if (stage == 1) { smem[3 * cs + c] = v; v = 0.0; }                         // summed over ranks before the clamp
-                else v = fmin(fmax(v, lm_min), lm_max) * scale;                            // clamp, then cumulative damping (A.4)
+        auto put = [&](int d, double val) {
+            if (d & 0x40000000) {
+                d &= 0x3fffffff;
+                if (stage == 1) { smem[d % ld] = val; val = 0.0; }                         // summed over ranks before the clamp
+                else val = fmin(fmax(val, lm_min), lm_max) * scale;                        // clamp, then cumulative damping (A.4)
             }
-            P[(3 * rs + r) + (3 * cs + c) * ld] = v;
+            P[d] = val;
+        };
+        {
+            double v[F3_PRE];
+#pragma unroll
+            for (int u = 0; u < F3_PRE; ++u) v[u] = odst[u] >= 0 ? ((osrc[u] & 1) ? Ho : Hd)[osrc[u] >> 1] : 0.0;
+#pragma unroll
+            for (int u = 0; u < F3_PRE; ++u)
+                if (odst[u] >= 0) put(odst[u], v[u]);
+        }
+        for (int idx = tid + F3_PRE * NT; idx < 9 * no; idx += NT) {   // fronts with more original entries than that
+            int so, d;
+            resolve(idx, so, d);
+            if (d >= 0) put(d, ((so & 1) ? Ho : Hd)[so >> 1]);
         }
         for (int idx = tid; idx < 3 * np; idx += NT) P[(Rf - 1) + idx * ld] = -g[3 * (size_t)vars[idx / 3] + idx % 3];
         for (int idx = 3 * np + tid; idx < Cf; idx += NT) {        // dummy pivots: identity, decoupled
@@ -150,33 +157,68 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     __syncthreads();
     PHASE(2);
 
-    // A2. extend-add of the children's update matrices: one warp per column of the child's packed lower triangle,
-    // up to four independent (coalesced) loads in flight per lane
-    for (int k = 0; k < nch; ++k) {
-        const int c = m.children[k0 + k];
-        if (stage == 1 && m.part[c] != m.mypart) continue;         // this rank's private children only
-        if (stage == 2 && m.part[c] >= 0) continue;                // shared children only
-        const int* cm = m.cmap + m.cmap_off[k0 + k];
-        const int ubc = 3 * m.nb[c] + 1;
-        const double* Uc = Ubuf + m.Uoff[c];
-        for (int cc = warp; cc < ubc - 1; cc += NW) {              // the last column is the unused (rhs, rhs) corner
-            const int pc = 3 * cm[cc / 3] + cc % 3;
-            const double* col = Uc + ((size_t)cc * ubc - (size_t)cc * (cc - 1) / 2 - cc);
-            for (int r0 = cc; r0 < ubc; r0 += 128) {
-                double v[4];
+    // A2. extend-add of the children's update matrices: a warp takes four columns of the child's packed lower triangle
+    // at a time (up to sixteen independent coalesced loads in flight per lane); children one after the other (fixed order)
+    {
+        int cm_off = 0;
+        for (int k = 0; k < nch; ++k) {
+            const int c = m.children[k0 + k];
+            const int nbc = m.nb[c], ubc = 3 * nbc + 1;
+            const int* cm = cm_staged ? scm + cm_off : m.cmap + m.cmap_off[k0 + k];
+            cm_off += nbc;
+            if (stage == 1 && m.part[c] != m.mypart) continue;         // this rank's private children only
+            if (stage == 2 && m.part[c] >= 0) continue;                // shared children only
+            const double* Uc = Ubuf + m.Uoff[c];
+            if (MODE == 2 && m.dmap != nullptr) {
+                // destinations precomputed on the host (offsets into [P | U] in shared memory, same packed order as the
+                // child's U): two coalesced streams, eight independent element pairs in flight per thread
+                const unsigned short* dm = m.dmap + m.Uoff[c];
+                const int n = (int)f3_ulen(ubc) - 1;                   // the last element is the unused (rhs, rhs) corner
+                for (int e0 = tid; e0 < n; e0 += 8 * NT) {
+                    double v[8];
+                    int d[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int r = r0 + lane + 32 * u; v[u] = r < ubc ? col[r] : 0.0; }
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * NT;
+                        v[u] = e < n ? Uc[e] : 0.0;
+                        d[u] = e < n ? (int)dm[e] : -1;
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = r0 + lane + 32 * u;
-                    if (r >= ubc) continue;
-                    const int pr = (r == ubc - 1) ? Rf - 1 : 3 * cm[r / 3] + r % 3;
-                    if (pc < Cf) P[pr + pc * ld] += v[u];
-                    else Uw[f3_uidx(pr - Cf, pc - Cf, ub)] += v[u];
+                    for (int u = 0; u < 8; ++u)
+                        if (d[u] >= 0) P[d[u]] += v[u];
+                }
+            } else
+            for (int cc0 = 4 * warp; cc0 < ubc - 1; cc0 += 4 * NW) {   // the last column is the unused (rhs, rhs) corner
+                for (int r0 = 0; cc0 + r0 < ubc; r0 += 128) {
+                    double v[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int cc = cc0 + j;
+                        const double* col = Uc + ((size_t)cc * ubc - (size_t)cc * (cc - 1) / 2 - cc);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = cc + r0 + lane + 32 * u;
+                            v[j][u] = (cc < ubc - 1 && r < ubc) ? col[r] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int cc = cc0 + j;
+                        if (cc >= ubc - 1) continue;
+                        const int pc = 3 * cm[cc / 3] + cc % 3;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = cc + r0 + lane + 32 * u;
+                            if (r >= ubc) continue;
+                            const int pr = (r == ubc - 1) ? Rf - 1 : 3 * cm[r / 3] + r % 3;
+                            if (pc < Cf) P[pr + pc * ld] += v[j][u];
+                            else Uw[f3_uidx(pr - Cf, pc - Cf, ub)] += v[j][u];
+                        }
+                    }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
     PHASE(3);
 
@@ -188,33 +230,136 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         return;
     }
 
-    // B. right-looking blocked Cholesky of the panel, 9 columns per step, with look-ahead: while warps 1.. apply block
-    // column jb to the trailing columns, warp 0 updates just the next 9x9 diagonal block, factors and inverts it (the
-    // serial part), so the single-warp latency hides behind the bulk update.  sLinv is double-buffered.
+    // B. right-looking blocked Cholesky of the panel, 9 columns per step.  The 9x9 diagonal blocks form the serial chain
+    // (update, Cholesky, inverse: warp 0); everything else is hidden in its shadow by warps 1..: the trailing update of
+    // the panel, the store of the finished block column to global memory, and the rank-9 contribution of that block
+    // column to the update matrix  U -= L21 L21^T  (so no separate Schur-complement phase remains).  sLinv is
+    // double-buffered.
     bool ok = true;
-    auto diag_block = [&](int jbn, double* Lout) {           // warp 0 only: P diag block (already updated) -> L, Linv
-        const int d0 = 9 * jbn;
-        double A[45], linv[9];
+    // warp 0 only.  Lane r < 9 owns row r of the 9x9 diagonal block jbn: (optionally) the rank-9 update from block column
+    // jbn-1, then a right-looking Cholesky with one shuffle per needed element, the rows of L back to the panel, and
+    // column `lane` of L^-1 by forward substitution with L streamed from shared memory.  ~35 registers, no spills on
+    // the serial chain.
+    auto diag_block = [&](int jbn, bool update, double* Lout) {
+        const int d0 = 9 * jbn, row = d0 + (lane < 9 ? lane : 0);
+        double a[9], linv[9];
 #pragma unroll
-        for (int r = 0; r < 9; ++r)
+        for (int q = 0; q < 9; ++q) a[q] = P[row + (d0 + q) * ld];
+        if (update) {
+            const int cprev = d0 - 9;
+            double w[9];
 #pragma unroll
-            for (int q = 0; q <= r; ++q) A[r * (r + 1) / 2 + q] = P[(d0 + r) + (d0 + q) * ld];
-        ok = chol9_rl(A, linv) && ok;
-        __syncwarp();
-        if (lane == 0) {
+            for (int k = 0; k < 9; ++k) w[k] = P[row + (cprev + k) * ld];
 #pragma unroll
-            for (int r = 0; r < 9; ++r)
+            for (int q = 0; q < 9; ++q) {
+                double s_ = 0.0;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) P[(d0 + r) + (d0 + q) * ld] = (q <= r) ? A[r * (r + 1) / 2 + (q <= r ? q : 0)] : 0.0;
+                for (int k = 0; k < 9; ++k) s_ += w[k] * P[(d0 + q) + (cprev + k) * ld];
+                a[q] -= s_;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            double d = __shfl_sync(0xffffffffu, a[c], c);
+            if (!(d > 0.0) || !(d < 1e300)) { ok = false; d = 1.0; }
+            const double inv = rsqrt(d);                       // <= 1 ulp; every lane redundantly
+            linv[c] = inv;
+            const double lc = (lane == c) ? d * inv : a[c] * inv;
+            a[c] = lc;
+#pragma unroll
+            for (int c2 = c + 1; c2 < 9; ++c2) a[c2] -= lc * __shfl_sync(0xffffffffu, lc, c2);
         }
         if (lane < 9) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                if (q <= lane) P[row + (d0 + q) * ld] = a[q];
+        }
+        __syncwarp();
+        if (lane < 9) {                                        // x = L^-1 e_lane, axpy form
             double x[9];
-            tri_inv_col_uniform(A, linv, lane, x);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                x[k] *= linv[k];
+#pragma unroll
+                for (int i = k + 1; i < 9; ++i) x[i] -= P[(d0 + i) + (d0 + k) * ld] * x[k];
+            }
 #pragma unroll
             for (int i = 0; i < 9; ++i) Lout[9 * i + lane] = x[i];
         }
     };
-    if (warp == 0) diag_block(0, sLinv);
+    // finished block column jb -> global factor (rows from its diagonal block down; nothing above is ever read)
+    auto store_block = [&](int jb, int t0, int nt) {
+        if (!P_SMEM) return;
+        const int c0 = 9 * jb, nr = Rf - c0;
+        for (int idx = t0; idx < 9 * nr; idx += nt) {
+            const int q = idx / nr, i = c0 + idx - q * nr;
+            Lg[i + (size_t)(c0 + q) * Rf] = P[i + (c0 + q) * ld];
+        }
+    };
+    // U -= L21[:, blocks] L21[:, blocks]^T over the lower triangle (+ rhs row), 4x4 register tiles.  Tiles are laid
+    // out on ABSOLUTE panel rows from R0 = Cf rounded down to even, so the LDS.128 operand pairs are 16-byte aligned
+    // whatever the parity of Cf (a tile row above Cf is computed and dropped).
+    const int R0 = Cf & ~1, shift = Cf - R0;
+    const int ntr = (ub + shift + 3) >> 2, ntiles = ub > 1 ? ntr * (ntr + 1) / 2 : 0;
+    auto tile_of = [&](int t, int& tr, int& tc) {
+        tr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+        while (tr * (tr + 1) / 2 > t) --tr;
+        tc = t - tr * (tr + 1) / 2;
+    };
+    int tr_first = 0, tc_first = 0;            // the first tile of this thread in the shadowed steps (threads 32..NT-1)
+    if (tid >= 32 && tid - 32 < ntiles) tile_of(tid - 32, tr_first, tc_first);
+    auto schur_blocks = [&](int jb0, int jb1, int t0, int nt) {     // block columns [jb0, jb1)
+        const int c0 = 9 * jb0, kn = 9 * (jb1 - jb0);
+        if (kn <= 0) return;
+        for (int t = t0; t < ntiles; t += nt) {
+            int tr, tc;
+            if (t == tid - 32) { tr = tr_first; tc = tc_first; }
+            else tile_of(t, tr, tc);
+            const int r0 = 4 * tr, s0 = 4 * tc;
+            double acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+            const double* pa = P + R0 + r0 + c0 * ld;
+            const double* pb = P + R0 + s0 + c0 * ld;
+#pragma unroll 3
+            for (int k = 0; k < kn; ++k) {
+                double av[4], bv[4];
+                if (P_SMEM) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(pa + k * ld);
+                    const double2 a23 = *reinterpret_cast<const double2*>(pa + k * ld + 2);
+                    const double2 b01 = *reinterpret_cast<const double2*>(pb + k * ld);
+                    const double2 b23 = *reinterpret_cast<const double2*>(pb + k * ld + 2);
+                    av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
+                    bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        av[x] = (R0 + r0 + x < Rf) ? pa[k * ld + x] : 0.0;
+                        bv[x] = (R0 + s0 + x < Rf) ? pb[k * ld + x] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int r = r0 + x - shift, s_ = s0 + y - shift;
+                    if (r >= 0 && s_ >= 0 && r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1))
+                        Uw[f3_uidx(r, s_, ub)] -= acc[x][y];
+                }
+        }
+    };
+    int pend_first = 0;                        // first finished block column not yet applied to U
+    if (warp == 0) diag_block(0, false, sLinv);
     __syncthreads();
     for (int jb = 0; jb < nbs; ++jb) {
         const int c0 = 9 * jb;
@@ -238,132 +383,70 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         }
         __syncthreads();
         PHASE(11 + 3 * jb);
-        // trailing update; warp 0 takes the next diagonal block (update + Cholesky + inverse), warps 1.. the rest
         const int ncb = nbs - 1 - jb;
-        if (ncb > 0) {
-            if (warp == 0) {
-                const int d0 = c0 + 9;
-                for (int e = lane; e < 45; e += 32) {            // lower triangle of the next diagonal block
-                    int r = 0;
-                    while ((r + 1) * (r + 2) / 2 <= e) ++r;
-                    const int q = e - r * (r + 1) / 2;
-                    double s_ = 0.0;
+        // finished block columns enter U two at a time (rank 18: half the read-modify-write passes over U), in the even
+        // steps from the third on, where the trailing update has become light; the rest in the last step
+        const bool schur_now = ncb == 0 || (jb >= 2 && (jb & 1) == 0);
+        const int schur_to = ncb == 0 ? nbs : jb;
+        if (ncb == 0) {                        // last block column: nothing left on the serial chain
+            store_block(jb, tid, NT);
+            schur_blocks(pend_first, schur_to, tid, NT);
+        } else if (warp == 0) {                // the serial chain: next diagonal block (update + Cholesky + inverse)
+            diag_block(jb + 1, true, sLinv + 96 * ((jb + 1) & 1));
+        } else {
+            // trailing update: column block cb only needs rows >= 9 cb (lower trapezoid); the 9 diagonal rows of block
+            // jb+1 are warp 0's
+            int tasks = 0;
+            for (int cb = jb + 1; cb < nbs; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
+            for (int t = tid - 32; t < tasks; t += NT - 32) {
+                int cb = jb + 1, rem = t;
+                while (rem >= 3 * ((Rf - 9 * cb + 3) >> 2)) { rem -= 3 * ((Rf - 9 * cb + 3) >> 2); ++cb; }
+                const int S = (Rf - 9 * cb + 3) >> 2;
+                const int c3 = rem / S, rt = rem - c3 * S;
+                const int j0 = 9 * cb, jc = j0 + 3 * c3;
+                int ix[4];
+                bool vx[4];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) s_ += P[(d0 + r) + (c0 + k) * ld] * P[(d0 + q) + (c0 + k) * ld];
-                    P[(d0 + r) + (d0 + q) * ld] -= s_;
+                for (int x = 0; x < 4; ++x) {
+                    ix[x] = j0 + rt + x * S;
+                    vx[x] = ix[x] < Rf && !(cb == jb + 1 && ix[x] < j0 + 9);
+                    if (!vx[x]) ix[x] = j0;
                 }
-                __syncwarp();
-                diag_block(jb + 1, sLinv + 96 * ((jb + 1) & 1));
-            } else {
-                // column block cb only needs rows >= 9 cb (lower trapezoid); the 9 diagonal rows of block jb+1 are warp 0's
-                int tasks = 0;
-                for (int cb = jb + 1; cb < nbs; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
-                for (int t = tid - 32; t < tasks; t += NT - 32) {
-                    int cb = jb + 1, rem = t;
-                    while (rem >= 3 * ((Rf - 9 * cb + 3) >> 2)) { rem -= 3 * ((Rf - 9 * cb + 3) >> 2); ++cb; }
-                    const int S = (Rf - 9 * cb + 3) >> 2;
-                    const int c3 = rem / S, rt = rem - c3 * S;
-                    const int j0 = 9 * cb, jc = j0 + 3 * c3;
-                    int ix[4];
-                    bool vx[4];
+                double acc[4][3];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        ix[x] = j0 + rt + x * S;
-                        vx[x] = ix[x] < Rf && !(cb == jb + 1 && ix[x] < j0 + 9);
-                        if (!vx[x]) ix[x] = j0;
-                    }
-                    double acc[4][3];
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const double* col = P + (c0 + q) * ld;
+                    double av[4], bv[3];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
+#pragma unroll
+                    for (int y = 0; y < 3; ++y) bv[y] = col[jc + y];
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
-                        for (int y = 0; y < 3; ++y) acc[x][y] = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) {
-                        const double* col = P + (c0 + q) * ld;
-                        double av[4], bv[3];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) av[x] = col[ix[x]];
-#pragma unroll
-                        for (int y = 0; y < 3; ++y) bv[y] = col[jc + y];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-#pragma unroll
-                            for (int y = 0; y < 3; ++y) acc[x][y] += av[x] * bv[y];
-                    }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-                        if (vx[x])
-#pragma unroll
-                            for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
+                        for (int y = 0; y < 3; ++y) acc[x][y] += av[x] * bv[y];
                 }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (vx[x])
+#pragma unroll
+                        for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
             }
+            store_block(jb, tid - 32, NT - 32);
+            if (schur_now) schur_blocks(pend_first, schur_to, tid - 32, NT - 32);
         }
+        if (schur_now) pend_first = schur_to;
         __syncthreads();
         PHASE(12 + 3 * jb);
     }
     if (!ok && tid == 0) *chol_fail = 1;
     PHASE(4);
-
-    // C. keep the factor for the back-substitution (global panel has leading dimension Rf)
-    for (int idx = tid; idx < Rf * Cf; idx += NT) {
-        const int j = idx / Rf, i = idx - j * Rf;
-        Lg[idx] = P[i + j * ld];
-    }
-#ifdef ISLAM_PHASE_CLOCKS
-    __syncthreads();
-#endif
-    PHASE(5);
-
-    // D. update matrix on the boundary (+ rhs row): U = (children's pass-through) - L21 L21^T.
-    // 4x4 register tiles over the lower triangle; operands are LDS.128 pairs: tiles are laid out on ABSOLUTE panel rows
-    // from R0 = Cf rounded down to even, so every row quad is 16-byte aligned whatever the parity of Cf (a tile row
-    // above Cf is computed and dropped).
-    if (ub > 1) {
-        const int R0 = Cf & ~1, shift = Cf - R0;
-        const int ntr = (ub + shift + 3) >> 2;
-        const int ntiles = ntr * (ntr + 1) / 2;
-        for (int t = tid; t < ntiles; t += NT) {
-            int tr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
-            while (tr * (tr + 1) / 2 > t) --tr;
-            const int tc = t - tr * (tr + 1) / 2;
-            const int r0 = 4 * tr, s0 = 4 * tc;
-            double acc[4][4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-            const double* pa = P + R0 + r0;
-            const double* pb = P + R0 + s0;
-#pragma unroll 4
-            for (int k = 0; k < Cf; ++k) {
-                const double2 a01 = *reinterpret_cast<const double2*>(pa + k * ld);
-                const double2 a23 = *reinterpret_cast<const double2*>(pa + k * ld + 2);
-                const double2 b01 = *reinterpret_cast<const double2*>(pb + k * ld);
-                const double2 b23 = *reinterpret_cast<const double2*>(pb + k * ld + 2);
-                const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
-            }
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int r = r0 + x - shift, s_ = s0 + y - shift;
-                    if (r >= 0 && s_ >= 0 && r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1)) {
-                        const int ui = f3_uidx(r, s_, ub);
-                        if (u_accumulates) Uw[ui] -= acc[x][y];
-                        else Uw[ui] = -acc[x][y];
-                    }
-                }
-        }
-        if (U_SMEM) {
-            __syncthreads();
-            for (int i = tid; i < ulen; i += NT) Ug[i] = Uw[i];
-        }
-    }
+    if (U_SMEM)
+        for (int i = tid; i < ulen; i += NT) Ug[i] = Uw[i];
 #ifdef ISLAM_PHASE_CLOCKS
     __syncthreads();
 #endif
