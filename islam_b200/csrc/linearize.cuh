@@ -86,8 +86,8 @@ __device__ __forceinline__ void rot_factor(const float* qi, const float* qj, con
 // mode 1: trial evaluation — residuals at the trial state (loss partials) and the unweighted
 //         (J D)^T (2 r + J D) term of TrustRegion.update from the stored linearisation
 template <int MODE>
-__global__ void __launch_bounds__(LIN_THREADS)
-k_vo(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+__device__ __forceinline__ void
+vo_block(int blk, const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
      ProblemView pv, LinBuffers lb, const double* __restrict__ D, double* __restrict__ part_out, int force) {
     if (!force) {
         if (!st->active) return;
@@ -97,7 +97,7 @@ k_vo(const LMState* __restrict__ st, const float* __restrict__ nodes0, const flo
     const float* nodes = (MODE == 0) ? (cur ? nodes1 : nodes0) : (cur ? nodes0 : nodes1);
     __shared__ double sh[LIN_THREADS / 32];
     __shared__ double sh2[LIN_THREADS / 32];
-    int e = blockIdx.x * LIN_THREADS + threadIdx.x;
+    int e = blk * LIN_THREADS + threadIdx.x;
     double lsum = 0.0, qsum = 0.0;
     bool mine = e < pv.E && (pv.edge_owner == nullptr || pv.edge_owner[e] == pv.part);
     if (mine) {
@@ -165,19 +165,19 @@ k_vo(const LMState* __restrict__ st, const float* __restrict__ nodes0, const flo
         }
     }
     double tot = block_sum<LIN_THREADS>(lsum, sh);
-    if (threadIdx.x == 0) part_out[2 * blockIdx.x] = tot;
+    if (threadIdx.x == 0) part_out[2 * blk] = tot;
     if (MODE == 1) {
         double tq = block_sum<LIN_THREADS>(qsum, sh2);
-        if (threadIdx.x == 0) part_out[2 * blockIdx.x + 1] = tq;
+        if (threadIdx.x == 0) part_out[2 * blk + 1] = tq;
     } else if (threadIdx.x == 0) {
-        part_out[2 * blockIdx.x + 1] = 0.0;
+        part_out[2 * blk + 1] = 0.0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------- IMU factors
 template <int MODE>
-__global__ void __launch_bounds__(LIN_THREADS)
-k_imu(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+__device__ __forceinline__ void
+imu_block(int blk, const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
       const float* __restrict__ vels0, const float* __restrict__ vels1, ProblemView pv, LinBuffers lb,
       const double* __restrict__ D, double* __restrict__ part_out, int force) {
     if (!force) {
@@ -189,7 +189,7 @@ k_imu(const LMState* __restrict__ st, const float* __restrict__ nodes0, const fl
     const float* vels = (MODE == 0) ? (cur ? vels1 : vels0) : (cur ? vels0 : vels1);
     __shared__ double sh[LIN_THREADS / 32];
     __shared__ double sh2[LIN_THREADS / 32];
-    int i = blockIdx.x * LIN_THREADS + threadIdx.x;
+    int i = blk * LIN_THREADS + threadIdx.x;
     double lsum = 0.0, qsum = 0.0;
     bool mine = i < pv.M && (pv.pair_owner == nullptr || pv.pair_owner[i] == pv.part);
     if (mine) {
@@ -235,13 +235,25 @@ k_imu(const LMState* __restrict__ st, const float* __restrict__ nodes0, const fl
         }
     }
     double tot = block_sum<LIN_THREADS>(lsum, sh);
-    if (threadIdx.x == 0) part_out[2 * blockIdx.x] = tot;
+    if (threadIdx.x == 0) part_out[2 * blk] = tot;
     if (MODE == 1) {
         double tq = block_sum<LIN_THREADS>(qsum, sh2);
-        if (threadIdx.x == 0) part_out[2 * blockIdx.x + 1] = tq;
+        if (threadIdx.x == 0) part_out[2 * blk + 1] = tq;
     } else if (threadIdx.x == 0) {
-        part_out[2 * blockIdx.x + 1] = 0.0;
+        part_out[2 * blk + 1] = 0.0;
     }
+}
+
+// one launch for both factor families: blocks [0, nblk_vo) take VO / loop-closure edges, the rest the IMU pairs
+template <int MODE>
+__global__ void __launch_bounds__(LIN_THREADS)
+k_factors(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+          const float* __restrict__ vels0, const float* __restrict__ vels1, ProblemView pv, LinBuffers lb,
+          const double* __restrict__ D, double* __restrict__ part_out, int nblk_vo, int force) {
+    cudaGridDependencySynchronize();           // PDL: only the launch latency overlaps the previous kernel
+    cudaTriggerProgrammaticLaunchCompletion();
+    if ((int)blockIdx.x < nblk_vo) vo_block<MODE>(blockIdx.x, st, nodes0, nodes1, pv, lb, D, part_out, force);
+    else imu_block<MODE>(blockIdx.x - nblk_vo, st, nodes0, nodes1, vels0, vels1, pv, lb, D, part_out + 2 * nblk_vo, force);
 }
 
 // ---------------------------------------------------------------------------------------------- assembly
@@ -257,11 +269,11 @@ struct AsmView {
 };
 
 // one warp per node: Hd[n] (9x9, full symmetric) and g[n] (9).  Fixed summation order => deterministic.
-__global__ void __launch_bounds__(128)
-k_assemble_nodes(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Hd,
+__device__ __forceinline__ void
+assemble_nodes_block(int blk, const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Hd,
                  double* __restrict__ g, int force) {
     if (!force && !(st->active && st->do_lin)) return;
-    int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int n = (blk * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (n >= pv.N) return;
     int e0 = av.node_eoff[n], e1 = av.node_eoff[n + 1];
@@ -342,11 +354,11 @@ k_assemble_nodes(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, 
 }
 
 // one warp per unique pair (lo < hi): Ho[p] = H[lo dofs, hi dofs]
-__global__ void __launch_bounds__(128)
-k_assemble_pairs(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Ho,
+__device__ __forceinline__ void
+assemble_pairs_block(int blk, const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Ho,
                  int force) {
     if (!force && !(st->active && st->do_lin)) return;
-    int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int p = (blk * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (p >= av.P) return;
     int lo = av.pair_lo[p];
@@ -379,6 +391,16 @@ k_assemble_pairs(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, 
         }
         Ho[81 * (size_t)p + idx] = v;
     }
+}
+
+// one launch for the block-diagonal and the off-diagonal part of J^T W J (one warp per 9x9 block either way)
+__global__ void __launch_bounds__(128)
+k_assemble(const LMState* __restrict__ st, ProblemView pv, LinBuffers lb, AsmView av, double* __restrict__ Hd,
+           double* __restrict__ Ho, double* __restrict__ g, int nblk_nodes, int force) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if ((int)blockIdx.x < nblk_nodes) assemble_nodes_block(blockIdx.x, st, pv, lb, av, Hd, g, force);
+    else assemble_pairs_block(blockIdx.x - nblk_nodes, st, pv, lb, av, Ho, force);
 }
 
 }  // namespace islam

@@ -9,6 +9,8 @@
 namespace islam {
 
 __global__ void k_begin_try(LMState* st) {
+    cudaGridDependencySynchronize();           // PDL: only the launch latency overlaps the previous kernel
+    cudaTriggerProgrammaticLaunchCompletion();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (!st->continual) { st->active = 0; return; }
     st->active = 1;
@@ -29,25 +31,45 @@ __global__ void __launch_bounds__(256) k_reduce2(const LMState* __restrict__ st,
     if (threadIdx.x == 0) { out[0] = s; out[1] = q; }
 }
 
-// opens the step / the try: cumulative damping of the (clamped) diagonal (A.4)
-__global__ void k_begin_step_a(LMState* st) {
-    if (threadIdx.x != 0 || !st->active) return;
-    if (st->do_lin) { st->reject_count = 0; st->diag_scale = 1.0; }
-    st->diag_scale *= (1.0 + st->damping);                                   // A.diag += A.diag * damping
-}
-
 // after the (possibly all-reduced) linearisation loss is known
-__global__ void k_begin_step_b(LMState* st, const double* __restrict__ lin_sum) {
-    if (threadIdx.x != 0 || !st->active || !st->do_lin) return;
+__device__ __forceinline__ void lm_begin_step_b(LMState* st, const double* __restrict__ lin_sum) {
+    if (!st->do_lin) return;
     st->lin_loss = lin_sum[0];
     if (!st->loss_valid) { st->loss = lin_sum[0]; st->loss_valid = 1; }      // first call: loss = model.loss()
     st->last = st->loss;
+}
+__global__ void k_begin_step_b(LMState* st, const double* __restrict__ lin_sum) {
+    if (threadIdx.x != 0 || !st->active) return;
+    lm_begin_step_b(st, lin_sum);
+}
+
+// opens the step / the try in ONE launch: deterministic sum of the linearisation partials, cumulative damping of the
+// (clamped) diagonal (A.4) and, on a single GPU (with_b), the bookkeeping that needs the linearisation loss
+__global__ void __launch_bounds__(256) k_begin_step(LMState* st, const double* __restrict__ part, int nparts,
+                                                    double* __restrict__ lin_sum, int with_b) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (!st->active) return;
+    __shared__ double sh[8], sh2[8];
+    if (st->do_lin) {
+        double s = 0.0, q = 0.0;
+        for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
+        s = block_sum<256>(s, sh);
+        q = block_sum<256>(q, sh2);
+        if (threadIdx.x == 0) { lin_sum[0] = s; lin_sum[1] = q; }
+    }
+    if (threadIdx.x != 0) return;
+    if (st->do_lin) { st->reject_count = 0; st->diag_scale = 1.0; }
+    st->diag_scale *= (1.0 + st->damping);                                   // A.diag += A.diag * damping
+    if (with_b) lm_begin_step_b(st, lin_sum);
 }
 
 // nodes <- Exp(d[:6]) nodes ; vels <- vels + d[6:9]   (LieTensor.add_ / update_parameter, A.1/A.4)
 __global__ void __launch_bounds__(128)
 k_retract(const LMState* __restrict__ st, float* nodes0, float* nodes1, float* vels0, float* vels1,
           const double* __restrict__ D, int N) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (!st->active) return;
     int cur = st->cur;
     const float* ns = cur ? nodes1 : nodes0;
@@ -82,10 +104,8 @@ __device__ __forceinline__ void lm_end_step(LMState* st, const islam_lm_params& 
 }
 
 // trial loss + trust-region update + accept / roll back
-__global__ void k_lm_control(LMState* st, const islam_lm_params* __restrict__ pp, const double* __restrict__ sums) {
-    if (threadIdx.x != 0 || !st->active) return;
+__device__ __forceinline__ void lm_control(LMState* st, const islam_lm_params* __restrict__ pp, double s, double q) {
     const islam_lm_params p = *pp;
-    const double s = sums[0], q = sums[1];
     st->loss_trial = s;
     if (st->chol_fail) {            // "Linear solver failed. Breaking optimization step..." : params untouched
         st->info = 1;
@@ -119,6 +139,26 @@ __global__ void k_lm_control(LMState* st, const islam_lm_params* __restrict__ pp
         st->accepted_last = 1;
         lm_end_step(st, p);
     }
+}
+__global__ void k_lm_control(LMState* st, const islam_lm_params* __restrict__ pp, const double* __restrict__ sums) {
+    if (threadIdx.x != 0 || !st->active) return;
+    lm_control(st, pp, sums[0], sums[1]);
+}
+
+// single GPU: closes the try in ONE launch — deterministic sum of the trial partials, then the controller
+__global__ void __launch_bounds__(256) k_end_try(LMState* st, const islam_lm_params* __restrict__ pp,
+                                                 const double* __restrict__ part, int nparts, double* __restrict__ sums) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (!st->active) return;
+    __shared__ double sh[8], sh2[8];
+    double s = 0.0, q = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
+    s = block_sum<256>(s, sh);
+    q = block_sum<256>(q, sh2);
+    if (threadIdx.x != 0) return;
+    sums[0] = s; sums[1] = q;
+    lm_control(st, pp, s, q);
 }
 
 // lm_reset without a host round trip: the parameters travel as a kernel argument into device memory, the state is

@@ -181,7 +181,8 @@ struct islam_pvgo {
     int nblk_vo = 0, nblk_imu = 0;
     // per level: kernel variant (solver3.cuh MODE | VAR_SMALL_CTA: 256-thread CTAs, two per SM),
     // dynamic shared memory of the factor / back-substitution kernels
-    std::vector<int> level_variant, level_smem_bytes, level_bs_bytes;
+    std::vector<int> level_variant, level_smem_bytes, level_bs_bytes, level_count;
+    int n_sm = 148;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
     std::vector<int> level_nlocal, level_nshared;
     std::vector<long long> h_shared_off;
@@ -220,7 +221,7 @@ extern "C" void islam_lm_default_params(islam_lm_params* p) {
 }
 
 // kernel variant of one level (islam_pvgo::level_variant): solver3.cuh MODE in bits 0-1 | VAR_SMALL_CTA
-enum { VAR_SMALL_CTA = 4 };
+enum { VAR_SMALL_CTA = 4, VAR_TINY_CTA = 8 };
 
 template <int NT, int MINB, int MODE> static void set_factor_smem(int bytes) {
     cudaFuncSetAttribute(k_factor3<NT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -344,9 +345,11 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if (max_optin <= 0) max_optin = 227 * 1024;
     set_factor_smem<512, 1, 2>(max_optin); set_factor_smem<512, 1, 1>(max_optin); set_factor_smem<512, 1, 0>(max_optin);
-    set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin);
+    set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin); set_factor_smem<128, 4, 1>(max_optin);
     cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     h->level_variant.assign(q.n_levels, 0);
+    h->level_count.assign(q.n_levels, 0);
+    h->n_sm = n_sm;
     h->level_smem_bytes.assign(q.n_levels, 0);
     h->level_bs_bytes.assign(q.n_levels, 0);
     {
@@ -365,10 +368,13 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         for (int l = 0; l < q.n_levels; ++l) {
             if (bs_min[l] > max_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
             int var = need[2][l] <= max_optin ? 2 : (need[1][l] <= max_optin ? 1 : 0);
-            const long long bytes = need[var][l];
-            // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency)
-            if (var > 0 && count[l] > n_sm && 2 * (bytes + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
+            long long bytes = need[var][l];
+            // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency);
+            // a leaf level wider than that: 128-thread CTAs, four per SM, update matrix written straight to global memory
+            if (l == 0 && count[l] > 2 * n_sm && 4 * (need[1][l] + 1024) <= smem_sm) { var = 1 | VAR_TINY_CTA; bytes = need[1][l]; }
+            else if (var > 0 && count[l] > n_sm && 2 * (bytes + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
             h->level_variant[l] = var;
+            h->level_count[l] = count[l];
             h->level_smem_bytes[l] = (int)bytes;
             h->level_bs_bytes[l] = (int)(bs_full[l] <= max_optin ? bs_full[l] : bs_min[l]);
         }
@@ -513,15 +519,26 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// kernel family 1 in two launches: all factors (residuals, Jacobian blocks, per-factor J^T W J), then the deterministic
+// assembly of the block-diagonal and off-diagonal 9x9 blocks
 static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan& p = h->plan;
-    double* part = h->lin_part.p;
-    if (h->nblk_vo)
-        k_vo<0><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, force);
-    k_imu<0><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
-                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, force);
-    k_assemble_nodes<<<(p.N * 32 + 127) / 128, 128, 0, s>>>(h->st.p, h->pv, h->lb, h->av, h->Hd.p, h->g.p, force);
-    k_assemble_pairs<<<(p.P * 32 + 127) / 128, 128, 0, s>>>(h->st.p, h->pv, h->lb, h->av, h->Ho.p, force);
+    CK(launch_pdl(k_factors<0>, h->nblk_vo + h->nblk_imu, LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
+                  (const float*)h->nodes[1].p, (const float*)h->vels[0].p, (const float*)h->vels[1].p, h->pv, h->lb,
+                  (const double*)h->D.p, h->lin_part.p, h->nblk_vo, force));
+    const int nbn = (p.N * 32 + 127) / 128, nbp = (p.P * 32 + 127) / 128;
+    CK(launch_pdl(k_assemble, nbn + nbp, 128, 0, s, (const LMState*)h->st.p, h->pv, h->lb, h->av, h->Hd.p, h->Ho.p, h->g.p, nbn, force));
+    return (int)cudaGetLastError();
+}
+
+// retraction to the trial state, trial residuals + quality term of the owned factors -> per-block partial sums
+static int launch_trial(islam_pvgo* h, cudaStream_t s) {
+    const Plan& p = h->plan;
+    CK(launch_pdl(k_retract, (p.N + 127) / 128, 128, 0, s, (const LMState*)h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
+                  h->vels[1].p, (const double*)h->D.p, p.N));
+    CK(launch_pdl(k_factors<1>, h->nblk_vo + h->nblk_imu, LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
+                  (const float*)h->nodes[1].p, (const float*)h->vels[0].p, (const float*)h->vels[1].p, h->pv, h->lb,
+                  (const double*)h->D.p, h->trial_part.p, h->nblk_vo, 0));
     return (int)cudaGetLastError();
 }
 
@@ -529,15 +546,21 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
 static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force);
 
 // `n` fronts of level l starting at d_level_fronts[first], in the given stage (solver3.cuh)
-static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int first, int n, double forced_scale, int stage) {
+static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int first, int n, double forced_scale, int stage,
+                                       int pre_ok) {
+    // Always let the next level start its preamble early.  Measured alternative (launch only when this level has drained
+    // whenever the two levels together outnumber the SMs, so that no two fronts share an SM): the 7-12 us of exposed
+    // launch latency cost more than the sharing.
+    const int trigger_early = 1;
     const islam_lm_params& q = h->prm;
     const size_t smem = (size_t)h->level_smem_bytes[l];
     const int var = h->level_variant[l];
 #define F3_LAUNCH(NT, MINB, US)                                                                                          \
     launch_pdl(k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
                h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \
-               h->shared.p, q.lm_min, q.lm_max, forced_scale, stage, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p)
+               h->shared.p, q.lm_min, q.lm_max, forced_scale, stage, pre_ok, trigger_early, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p)
     switch (var) {
+        case 1 | VAR_TINY_CTA: return F3_LAUNCH(128, 4, 1);
         case 2 | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, 2);
         case 2: return F3_LAUNCH(512, 1, 2);
         case 1 | VAR_SMALL_CTA: return F3_LAUNCH(256, 2, 1);
@@ -549,8 +572,9 @@ static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int
 
 static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
     const Plan3& p = h->p3;
+    int launched = 0;                          // pre_ok: the previous kernel in the stream is a factor level of this sequence
     for (int l = 0; l < p.n_levels; ++l)
-        if (h->level_nlocal[l] > 0) CK(launch_factor_level(h, s, l, p.level_off[l], h->level_nlocal[l], forced_scale, 0));
+        if (h->level_nlocal[l] > 0) CK(launch_factor_level(h, s, l, p.level_off[l], h->level_nlocal[l], forced_scale, 0, launched++ > 0));
     int rc = launch_root_factor(h, s, forced_scale);
     if (rc) return rc;
     return (int)cudaGetLastError();
@@ -598,21 +622,24 @@ static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force) {
 // stage 1 = partial frontal matrices into the all-reduce buffer, stage 2 = factorisation after the all-reduce
 static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_scale, int stage) {
     const Plan3& p = h->p3;
+    int launched = 0;
     for (int l = 0; l < p.n_levels; ++l)
         if (h->level_nshared[l] > 0)
-            CK(launch_factor_level(h, s, l, p.level_off[l] + h->level_nlocal[l], h->level_nshared[l], forced_scale, stage));
+            CK(launch_factor_level(h, s, l, p.level_off[l] + h->level_nlocal[l], h->level_nshared[l], forced_scale, stage,
+                                   stage == 1 && launched++ > 0));
     return (int)cudaGetLastError();
 }
 
 static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan3& p = h->p3;
     { int rc = launch_root_solve(h, s, force); if (rc) return rc; }
+    int launched = 0;                          // pre_ok: the previous kernel in the stream is the parent level's back-substitution
     for (int l = p.n_levels - 1; l >= 0; --l) {
         int n = h->level_nlocal[l] + h->level_nshared[l];
         if (!n) continue;
         CK(launch_pdl(k_backsolve3, n, BS3_THREADS, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
                       (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
-                      h->D.p, force, h->level_bs_bytes[l] / 8));
+                      h->D.p, force, h->level_bs_bytes[l] / 8, launched++ > 0));
     }
     return (int)cudaGetLastError();
 }
@@ -683,14 +710,19 @@ static double* lin_sum_ptr(islam_pvgo* h) {          // single GPU: private scra
 }
 static double* trial_sum_ptr(islam_pvgo* h) { return h->sums.p + 4; }
 
-static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
+// phase A: open the try, linearise if a new step starts, sum the loss partials, damp
+static int enqueue_open(islam_pvgo* h, cudaStream_t s) {
     const int np_ = h->nblk_vo + h->nblk_imu;
-    k_begin_try<<<1, 32, 0, s>>>(h->st.p);
+    CK(launch_pdl(k_begin_try, 1, 32, 0, s, h->st.p));
     int rc = launch_linearize(h, s, 0);
     if (rc) return rc;
-    k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, np_, lin_sum_ptr(h), 1);
-    k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
-    if (h->opts.n_parts == 1) k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
+    CK(launch_pdl(k_begin_step, 1, 256, 0, s, h->st.p, (const double*)h->lin_part.p, np_, lin_sum_ptr(h), (int)(h->opts.n_parts == 1)));
+    return (int)cudaGetLastError();
+}
+
+static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
+    int rc = enqueue_open(h, s);
+    if (rc) return rc;
     rc = launch_factor(h, s, 0.0);
     if (rc) return rc;
     if (h->opts.n_parts > 1 && h->n_shared > 0) return launch_factor_shared(h, s, 0.0, 1);
@@ -699,7 +731,6 @@ static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
 
 // after the all-reduce of the shared panels (multi-GPU) / directly (single GPU): finish the solve, evaluate the trial
 static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
-    const Plan& p = h->plan;
     const int np_ = h->nblk_vo + h->nblk_imu;
     int rc = 0;
     if (h->opts.n_parts > 1) {
@@ -709,18 +740,17 @@ static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
     }
     rc = launch_backsolve(h, s, 0);
     if (rc) return rc;
-    k_retract<<<(p.N + 127) / 128, 128, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->D.p, p.N);
-    double* part = h->trial_part.p;
-    if (h->nblk_vo)
-        k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
-    k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
-                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
-    k_reduce2<<<1, 256, 0, s>>>(h->st.p, part, np_, trial_sum_ptr(h), 0);
+    rc = launch_trial(h, s);
+    if (rc) return rc;
+    if (h->opts.n_parts > 1) k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->trial_part.p, np_, trial_sum_ptr(h), 0);   // then all-reduced
     return (int)cudaGetLastError();
 }
 
 static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
-    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
+    const int np_ = h->nblk_vo + h->nblk_imu;
+    if (h->opts.n_parts > 1) k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
+    else CK(launch_pdl(k_end_try, 1, 256, 0, s, h->st.p, (const islam_lm_params*)h->d_prm.p, (const double*)h->trial_part.p, np_,
+                       trial_sum_ptr(h)));
     return (int)cudaGetLastError();
 }
 
@@ -730,30 +760,18 @@ extern "C" int islam_pvgo_profile_try(islam_pvgo* h, float* ms /* [5]: linearise
     if (!h || !ms) return -1;
     if (h->opts.n_parts > 1) return -6;
     cudaStream_t s = (cudaStream_t)stream;
-    const Plan& p = h->plan;
-    const int np_ = h->nblk_vo + h->nblk_imu;
     cudaEvent_t ev[5];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     int rc = 0;
     CK(cudaEventRecord(ev[0], s));
-    k_begin_try<<<1, 32, 0, s>>>(h->st.p);
-    rc = launch_linearize(h, s, 0);
-    k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->lin_part.p, np_, lin_sum_ptr(h), 1);
-    k_begin_step_a<<<1, 32, 0, s>>>(h->st.p);
-    k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
+    rc = enqueue_open(h, s);
     CK(cudaEventRecord(ev[1], s));
     if (!rc) rc = launch_factor(h, s, 0.0);
     CK(cudaEventRecord(ev[2], s));
     if (!rc) rc = launch_backsolve(h, s, 0);
     CK(cudaEventRecord(ev[3], s));
-    k_retract<<<(p.N + 127) / 128, 128, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->D.p, p.N);
-    double* part = h->trial_part.p;
-    if (h->nblk_vo)
-        k_vo<1><<<h->nblk_vo, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->pv, h->lb, h->D.p, part, 0);
-    k_imu<1><<<h->nblk_imu, LIN_THREADS, 0, s>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p, h->vels[1].p, h->pv,
-                                                  h->lb, h->D.p, part + 2 * h->nblk_vo, 0);
-    k_reduce2<<<1, 256, 0, s>>>(h->st.p, part, np_, trial_sum_ptr(h), 0);
-    k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
+    if (!rc) rc = launch_trial(h, s);
+    if (!rc) rc = enqueue_try_end(h, s);
     CK(cudaEventRecord(ev[4], s));
     CK(cudaStreamSynchronize(s));
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
@@ -947,6 +965,10 @@ extern "C" int64_t islam_plan_array(const islam_plan* pl, const char* name, cons
 
 #ifdef ISLAM_PHASE_CLOCKS
 extern "C" int islam_debug_phase_grid(int g) { return (int)cudaMemcpyToSymbol(islam::g_phase_grid, &g, sizeof(int)); }
+extern "C" int islam_debug_front_times(unsigned long long* out /* [4][8192] */) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, islam::g_front_t, sizeof(unsigned long long) * 4 * 8192);
+}
 extern "C" int islam_debug_phase_clocks(long long* out64) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out64, islam::g_phase_clk, sizeof(long long) * 64);

@@ -21,9 +21,15 @@ namespace islam {
 #ifdef ISLAM_PHASE_CLOCKS
 __device__ long long g_phase_clk[64];
 __device__ int g_phase_grid = 1;
-#define PHASE(n) do { if (blockIdx.x == 0 && threadIdx.x == 0 && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
+#define PHASE(n) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
+// per front: globaltimer at CTA start, after the grid dependency, at the end; SM id  (tools/level_timeline.py)
+__device__ unsigned long long g_front_t[4][8192];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#define FRONT_T(k, f) do { if (threadIdx.x == 0 && (f) < 8192) g_front_t[k][f] = (k) == 3 ? (unsigned long long)smid() : gtime(); } while (0)
 #else
 #define PHASE(n) do { } while (0)
+#define FRONT_T(k, f) do { } while (0)
 #endif
 
 constexpr int F3_HEAD = 192 + 128;   // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
@@ -54,15 +60,18 @@ __global__ void __launch_bounds__(NT, MINB)
 k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3Meta m,
           const double* __restrict__ Hd, const double* __restrict__ Ho, const double* __restrict__ g,
           double* __restrict__ Lbuf, double* __restrict__ Ubuf, double* __restrict__ Linv,
-          double* __restrict__ shared, double lm_min_, double lm_max_, double forced_scale, int stage,
-          int* chol_fail, const islam_lm_params* __restrict__ prm) {
-    // Launched with programmatic stream serialisation (PDL): everything up to cudaGridDependencySynchronize() only
-    // touches the immutable symbolic plan and this CTA's shared memory, so it overlaps the tail of the previous level.
+          double* __restrict__ shared, double lm_min_, double lm_max_, double forced_scale, int stage, int pre_ok,
+          int trigger_early, int* chol_fail, const islam_lm_params* __restrict__ prm) {
+    // Launched with programmatic stream serialisation (PDL): everything up to cudaGridDependencySynchronize() overlaps the
+    // tail of the previous level.  That is always the zero fill and the resolution of the immutable maps; with pre_ok
+    // (the previous kernel in the stream is another factor level, so the LM state, J^T W J and J^T W r were complete
+    // before IT started) also the whole of A1, the original entries.
     constexpr bool P_SMEM = MODE >= 1, U_SMEM = MODE == 2;
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
     PHASE(0);
+    FRONT_T(0, f); FRONT_T(3, f);
     extern __shared__ double smem[];
     double* sLinv = smem;                      // 2 x 81 (+ pad): double-buffered inverse diagonal blocks
     const int np = m.np[f], npad = m.npad[f], nb = m.nb[f];
@@ -104,28 +113,24 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     const bool cm_staged = cm_total <= F3_CMAP_INTS;
     if (cm_staged)
         for (int i = tid; i < cm_total; i += NT) scm[i] = m.cmap[m.cmap_off[k0] + i];       // children's maps are contiguous
-    cudaGridDependencySynchronize();           // previous level (children's U, LM state) complete and visible
-    cudaTriggerProgrammaticLaunchCompletion(); // the next level may start its preamble
-    if (forced_scale == 0.0 && !st->active) return;
-    const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
-    const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
-    if (!P_SMEM)
-        for (int i = tid; i < Rf * Cf; i += NT) P[i] = 0.0;
-    if (!U_SMEM)                               // the update matrix accumulates in place in global memory
-        for (int i = tid; i < ulen; i += NT) Ug[i] = 0.0;
-    __syncthreads();
-    PHASE(1);
-
+    double scale = 1.0, lm_min = 0.0, lm_max = 0.0;
+    bool active = true;
+    auto load_state = [&]() {
+        active = !(forced_scale == 0.0 && !st->active);
+        scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
+        lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min;
+        lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
+    };
     // A1. original entries of J^T W J / -J^T W r first touched by this front (disjoint destinations)
-    if (stage != 2) {
-        auto put = [&](int d, double val) {
-            if (d & 0x40000000) {
-                d &= 0x3fffffff;
-                if (stage == 1) { smem[d % ld] = val; val = 0.0; }                         // summed over ranks before the clamp
-                else val = fmin(fmax(val, lm_min), lm_max) * scale;                        // clamp, then cumulative damping (A.4)
-            }
-            P[d] = val;
-        };
+    auto put = [&](int d, double val) {
+        if (d & 0x40000000) {
+            d &= 0x3fffffff;
+            if (stage == 1) { smem[d % ld] = val; val = 0.0; }                             // summed over ranks before the clamp
+            else val = fmin(fmax(val, lm_min), lm_max) * scale;                            // clamp, then cumulative damping (A.4)
+        }
+        P[d] = val;
+    };
+    auto assemble_orig = [&]() {
         {
             double v[F3_PRE];
 #pragma unroll
@@ -144,7 +149,30 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             if (stage == 1) smem[idx] = 0.0;
             else P[idx + idx * ld] = 1.0;
         }
-    } else {
+    };
+    const bool pre = pre_ok && P_SMEM && stage != 2;
+    if (pre) {
+        __syncthreads();                       // zero fill complete
+        load_state();
+        if (active) assemble_orig();
+    }
+    cudaGridDependencySynchronize();           // previous level (children's U, LM state) complete and visible
+    // the next level may start its preamble now, unless its CTAs would have to squeeze in beside this level's (host's
+    // call: more fronts in the two levels together than SMs); then it launches when this level has drained
+    if (trigger_early) cudaTriggerProgrammaticLaunchCompletion();
+    FRONT_T(1, f);
+    if (!pre) load_state();
+    if (!active) return;
+    if (!P_SMEM)
+        for (int i = tid; i < Rf * Cf; i += NT) P[i] = 0.0;
+    // a leaf whose update matrix stays in global memory writes it once, at the end (U = -L21 L21^T); otherwise it
+    // accumulates in place: children's pass-through first, then the Schur contributions
+    const bool u_direct = !U_SMEM && nch == 0 && stage == 0;
+    if (!U_SMEM && !u_direct)
+        for (int i = tid; i < ulen; i += NT) Ug[i] = 0.0;
+    __syncthreads();
+    PHASE(1);
+    if (stage == 2) {
         const double* base = shared + m.shared_off[f];
         for (int idx = tid; idx < Rf * Cf; idx += NT) {
             const int j = idx / Rf, i = idx - j * Rf;
@@ -153,6 +181,8 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             P[i + j * ld] = v;
         }
         for (int idx = tid; idx < ulen; idx += NT) Uw[idx] = base[(size_t)Rf * Cf + idx];
+    } else if (!pre) {
+        assemble_orig();
     }
     __syncthreads();
     PHASE(2);
@@ -353,8 +383,11 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                     const int r = r0 + x - shift, s_ = s0 + y - shift;
-                    if (r >= 0 && s_ >= 0 && r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1))
-                        Uw[f3_uidx(r, s_, ub)] -= acc[x][y];
+                    if (r >= 0 && s_ >= 0 && r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1)) {
+                        const int ui = f3_uidx(r, s_, ub);
+                        if (u_direct) Uw[ui] = -acc[x][y];
+                        else Uw[ui] -= acc[x][y];
+                    }
                 }
         }
     };
@@ -386,7 +419,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         const int ncb = nbs - 1 - jb;
         // finished block columns enter U two at a time (rank 18: half the read-modify-write passes over U), in the even
         // steps from the third on, where the trailing update has become light; the rest in the last step
-        const bool schur_now = ncb == 0 || (jb >= 2 && (jb & 1) == 0);
+        const bool schur_now = ncb == 0 || (!u_direct && jb >= 2 && (jb & 1) == 0);
         const int schur_to = ncb == 0 ? nbs : jb;
         if (ncb == 0) {                        // last block column: nothing left on the serial chain
             store_block(jb, tid, NT);
@@ -451,6 +484,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     __syncthreads();
 #endif
     PHASE(6);
+    FRONT_T(2, f);
 }
 
 // ---- back-substitution of one level (root first) ---------------------------------------------------------------------
@@ -467,7 +501,7 @@ __host__ __device__ __forceinline__ long long bs3_smem_doubles(int Rf, int Cf, b
 __global__ void __launch_bounds__(BS3_THREADS)
 k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3Meta m,
              const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force,
-             int smem_doubles) {
+             int smem_doubles, int pre_ok) {
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NW = BS3_THREADS / 32;
@@ -482,13 +516,19 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     double* sLi = xs + 16;             // [nbs][81] inverse diagonal blocks
     double* sP = sLi + 81 * nbs;       // [Rf x Cf] panel copy (if it fits)
     const bool staged = (bs3_smem_doubles(Rf, Cf, true) <= smem_doubles);
+    // pre_ok: the previous kernel in the stream is the parent level of this very back-substitution, so the factor (L,
+    // Linv) was complete before it started: the panel is pulled into shared memory while the parents are still solving
+    auto stage_factor = [&]() {
+        for (int i = tid; i < 81 * nbs; i += BS3_THREADS) sLi[i] = Linv[m.Ioff[f] + i];
+        if (staged)
+            for (int i = tid; i < Rf * Cf; i += BS3_THREADS) sP[i] = Lg[i];
+    };
+    if (pre_ok) stage_factor();
     cudaGridDependencySynchronize();           // PDL: the parents' solution (and, for the root, the factor) is complete
     cudaTriggerProgrammaticLaunchCompletion();
     if (!force && !st->active) return;
     for (int r = tid; r < Rb; r += BS3_THREADS) xb[r] = D[3 * (size_t)vars[npad + r / 3] + (r % 3)];
-    for (int i = tid; i < 81 * nbs; i += BS3_THREADS) sLi[i] = Linv[m.Ioff[f] + i];
-    if (staged)
-        for (int i = tid; i < Rf * Cf; i += BS3_THREADS) sP[i] = Lg[i];
+    if (!pre_ok) stage_factor();
     const double* Lp = staged ? sP : Lg;
     __syncthreads();
     // ts[c] = y[c] - sum_r L21[r,c] xb[r]      (one warp per column)
