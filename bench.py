@@ -264,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
                                f'{LM_ITERS} fixed LM iterations per step, loss_weight (1,0.1,10,0.1), radius 1e4',
                    'parallelism': 'single GPU' if world == 1 else
                    f'{world} contiguous pose windows of ONE C2 graph; per LM try one NCCL all-reduce of the shared separator panels '
-                   f'({s.dims.n_shared_fronts} fronts, {s.dims.shared_doubles * 8 / 1e6:.2f} MB) + one 16-byte all-reduce of the trial loss',
+                   f'({s.dims.n_shared_fronts} fronts, {s.dims.shared_doubles * 8 / 1e6:.2f} MB); the trial sums travel through NVLink peer mailboxes inside the kernel that closes the try',
                    'l2': f'working set (L {s.dims.L_doubles * 8 / 1e6:.0f} MB + U {s.dims.U_doubles * 8 / 1e6:.0f} MB '
                          'fp64 panels) exceeds the 126 MB L2; no explicit flush'},
         'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,

@@ -133,14 +133,21 @@ int islam_pvgo_profile_try(islam_pvgo* h, float* ms, void* stream);
  *   -> all-reduce(SUM) of islam_pvgo_shared_buffer   (the per-try exchange of separator J^T W J / J^T W r blocks)
  *   try_mid   : factor the shared fronts (redundantly, identical on every rank), back-substitute, retract, evaluate
  *               the trial residuals of the owned factors -> 2 partial sums
- *   -> all-reduce(SUM) of islam_pvgo_sums_buffer     (2 doubles: trial sum r^2 and the quality term)
- *   try_end   : trust-region update + accept / roll back (identical decision on every rank)
+ *   try_end   : exchange of the 2 trial sums (sum r^2, quality term) + trust-region update + accept / roll back
+ *               (identical decision on every rank).  With peer mailboxes connected (islam_pvgo_mailbox_*: CUDA IPC, ranks
+ *               on one node) the exchange happens INSIDE the try_end kernel by direct NVLink stores into the peers'
+ *               memory: the all-reduce above is the only collective of the try.  Without them the caller all-reduces
+ *               islam_pvgo_sums_buffer between try_mid and try_end.
  * With n_parts == 1 the three calls in sequence are exactly islam_pvgo_lm_try. */
 int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream);
 int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
 int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream);
 int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
 int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
+/* peer mailboxes: every rank exports the IPC handle of its mailbox (64 bytes), the caller all-gathers them (rank order)
+ * and hands the table to every rank.  LM state info = 2 reports a peer that never answered (2 s timeout). */
+int islam_pvgo_mailbox_export(islam_pvgo* h, void* handle_out /* 64 bytes */);
+int islam_pvgo_mailbox_connect(islam_pvgo* h, const void* handles /* n_parts x 64 bytes */);
 /* owner window of every 3-dof variable (host array of 3N int32, [tau, phi, v] per pose): >= 0 private to that rank,
  * -1 shared / replicated (solved redundantly on every rank) */
 int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host);

@@ -71,6 +71,8 @@ _SIGS = {
     'islam_pvgo_sums_buffer': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     'islam_pvgo_lm_try_end': (C.c_int, [_P, _P]),
     'islam_pvgo_var_parts': (C.c_int, [_P, _P]),
+    'islam_pvgo_mailbox_export': (C.c_int, [_P, _P]),
+    'islam_pvgo_mailbox_connect': (C.c_int, [_P, _P]),
     'islam_pvgo_vo_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'islam_pvgo_imu_loss': (C.c_int, [_P, _P, _P, _P]),
     'islam_pvgo_align': (C.c_int, [_P, _P, _P, _P, _P]),

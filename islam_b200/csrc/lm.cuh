@@ -161,6 +161,58 @@ __global__ void __launch_bounds__(256) k_end_try(LMState* st, const islam_lm_par
     lm_control(st, pp, s, q);
 }
 
+// multi-GPU: closes the try in ONE launch and WITHOUT a second collective.  Every rank sums its trial partials, writes the
+// two doubles (trial sum r^2, quality term) straight into every peer's mailbox over NVLink (CUDA IPC peer memory), waits
+// for the G messages of this try, adds them in rank order (identical, deterministic result everywhere) and runs the
+// controller.  The mailbox is double-buffered on the try sequence number: a rank can run at most one exchange ahead of a
+// peer, because it cannot finish exchange k+1 before that peer has sent its message k+1, i.e. after it consumed message k.
+// mailbox layout (per rank, in its own device memory): [2 slots][G senders] x {s, q, seq, pad} (4 x 8 bytes)
+__global__ void __launch_bounds__(256) k_end_try_p2p(LMState* st, const islam_lm_params* __restrict__ pp,
+                                                     const double* __restrict__ part, int nparts, double* __restrict__ sums,
+                                                     unsigned long long* const* __restrict__ peers,
+                                                     unsigned long long* __restrict__ seq_ctr, int rank, int G) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (!st->active) return;
+    __shared__ double sh[8], sh2[8], in_s[64], in_q[64];
+    __shared__ unsigned long long seq_s;
+    __shared__ double my[2];
+    __shared__ int failed;
+    const int tid = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int k = tid; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
+    s = block_sum<256>(s, sh);
+    q = block_sum<256>(q, sh2);
+    if (tid == 0) { my[0] = s; my[1] = q; seq_s = ++(*seq_ctr); failed = 0; }
+    __syncthreads();
+    const unsigned long long seq = seq_s;
+    const int slot = (int)(seq & 1);
+    if (tid < G) {                                             // one thread per peer: payload, fence, then the flag
+        volatile unsigned long long* m = peers[tid] + (size_t)(slot * G + rank) * 4;
+        m[0] = (unsigned long long)__double_as_longlong(my[0]);
+        m[1] = (unsigned long long)__double_as_longlong(my[1]);
+        __threadfence_system();
+        m[2] = seq;
+    }
+    if (tid < G) {                                             // one thread per sender
+        volatile unsigned long long* m = peers[rank] + (size_t)(slot * G + tid) * 4;
+        const long long t0 = clock64();
+        while (m[2] != seq) {
+            if (clock64() - t0 > (4LL << 30)) { failed = 1; break; }        // ~2 s: a peer is gone
+        }
+        __threadfence_system();
+        in_s[tid] = __longlong_as_double((long long)m[0]);
+        in_q[tid] = __longlong_as_double((long long)m[1]);
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    if (failed) { st->info = 2; st->continual = 0; return; }
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < G; ++r) { S += in_s[r]; Q += in_q[r]; }
+    sums[0] = S; sums[1] = Q;
+    lm_control(st, pp, S, Q);
+}
+
 // lm_reset without a host round trip: the parameters travel as a kernel argument into device memory, the state is
 // re-initialised in place (the current/trial buffer index survives)
 __global__ void k_lm_reset(LMState* st, islam_lm_params* dst, islam_lm_params p) {

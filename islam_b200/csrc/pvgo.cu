@@ -172,6 +172,11 @@ struct islam_pvgo {
     DevBuf<long long> d_Loff, d_Uoff, d_Ioff, d_shared_off;
     DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
     DevBuf<unsigned short> d_dmap;
+    // multi-GPU: peer mailboxes for the trial sums (k_end_try_p2p)
+    DevBuf<unsigned long long> mail, mail_seq;
+    DevBuf<unsigned long long*> d_peers;
+    std::vector<void*> peer_mapped;           // cudaIpcOpenMemHandle mappings to close
+    bool p2p = false;
     RootView rv;
     bool has_root = false;
     DevBuf<LMState> st;
@@ -193,6 +198,8 @@ struct islam_pvgo {
 
     ~islam_pvgo() {
         if (graph_try) cudaGraphExecDestroy(graph_try);
+        for (void* p : peer_mapped) cudaIpcCloseMemHandle(p);
+        mail.release(); mail_seq.release(); d_peers.release();
         if (st_host) cudaFreeHost(st_host);
         DevBuf<int>* ib[] = {&ei, &ej, &edge_owner, &pair_owner, &d_node_eoff, &d_node_edges, &d_pair_lo, &d_pair_hi,
                              &d_pair_adj, &d_pair_eoff, &d_pair_edges, &d_np, &d_npad, &d_nb, &d_vars_off, &d_vars,
@@ -742,13 +749,17 @@ static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
     if (rc) return rc;
     rc = launch_trial(h, s);
     if (rc) return rc;
-    if (h->opts.n_parts > 1) k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->trial_part.p, np_, trial_sum_ptr(h), 0);   // then all-reduced
+    if (h->opts.n_parts > 1 && !h->p2p)
+        k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->trial_part.p, np_, trial_sum_ptr(h), 0);   // then all-reduced by the caller
     return (int)cudaGetLastError();
 }
 
 static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
     const int np_ = h->nblk_vo + h->nblk_imu;
-    if (h->opts.n_parts > 1) k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
+    if (h->opts.n_parts > 1 && h->p2p)
+        CK(launch_pdl(k_end_try_p2p, 1, 256, 0, s, h->st.p, (const islam_lm_params*)h->d_prm.p, (const double*)h->trial_part.p, np_,
+                      trial_sum_ptr(h), (unsigned long long* const*)h->d_peers.p, h->mail_seq.p, h->opts.part, h->opts.n_parts));
+    else if (h->opts.n_parts > 1) k_lm_control<<<1, 32, 0, s>>>(h->st.p, h->d_prm.p, trial_sum_ptr(h));
     else CK(launch_pdl(k_end_try, 1, 256, 0, s, h->st.p, (const islam_lm_params*)h->d_prm.p, (const double*)h->trial_part.p, np_,
                        trial_sum_ptr(h)));
     return (int)cudaGetLastError();
@@ -819,6 +830,41 @@ extern "C" int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* 
     *n = 2;
     return 0;
 }
+// ---- peer mailboxes (multi-GPU, one process per GPU on one node): CUDA IPC handles travel through the caller --------------
+extern "C" int islam_pvgo_mailbox_export(islam_pvgo* h, void* handle_out /* 64 bytes */) {
+    if (!h || !handle_out || h->opts.n_parts < 2 || h->opts.n_parts > 64) return -1;
+    const size_t n = 2 * (size_t)h->opts.n_parts * 4;
+    if (!h->mail.p) {
+        CK(h->mail.alloc(n));
+        CK(cudaMemset(h->mail.p, 0, n * sizeof(unsigned long long)));
+        CK(h->mail_seq.alloc(1));
+        CK(cudaMemset(h->mail_seq.p, 0, sizeof(unsigned long long)));
+    }
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h->mail.p));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out, &hd, sizeof(hd));
+    return 0;
+}
+
+extern "C" int islam_pvgo_mailbox_connect(islam_pvgo* h, const void* handles /* n_parts x 64 bytes, rank order */) {
+    if (!h || !handles || !h->mail.p) return -1;
+    const int G = h->opts.n_parts;
+    std::vector<unsigned long long*> ptrs(G, nullptr);
+    for (int r = 0; r < G; ++r) {
+        if (r == h->opts.part) { ptrs[r] = h->mail.p; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, (const char*)handles + 64 * (size_t)r, sizeof(hd));
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_mapped.push_back(p);
+        ptrs[r] = (unsigned long long*)p;
+    }
+    CK(h->d_peers.upload(ptrs));
+    h->p2p = true;
+    return 0;
+}
+
 // owner window of every 3-dof variable (3N: tau, phi, v per pose): >= 0 private to that rank, -1 shared
 extern "C" int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host) {
     if (!h || !out_host) return -1;

@@ -1,10 +1,12 @@
 """Multi-GPU PVGO: contiguous pose windows, one process per GPU, torch.distributed (NCCL over NVLink) for the exchange.
 
 SURVEY.md section 8e: the top log2(G) levels of the nested-dissection tree are the cuts between windows.  Every rank
-owns the factors that touch its private poses, eliminates its own subtree, and contributes partial panels of the
-shared (separator) fronts; ONE all-reduce per LM try sums those panels (plus the partial linearisation loss), after
-which every rank factors the few shared fronts redundantly and back-substitutes its own window.  A second, 2-double
-all-reduce carries the trial loss / quality term so that all ranks take the same accept / roll-back decision.
+owns the factors that touch its private variables, eliminates its own subtree, and contributes partial frontal matrices
+of the shared (separator) fronts; ONE NCCL all-reduce per LM try sums those (plus the partial linearisation loss), after
+which every rank factors the few shared fronts redundantly and back-substitutes its own window.  The two doubles every
+rank needs for the common accept / roll-back decision (trial loss, quality term) do not go through a second collective:
+the kernel that closes the try stores them straight into the peers' mailboxes over NVLink (CUDA IPC peer memory) and
+sums the G messages in rank order (exchange='p2p', the default; exchange='nccl' keeps a 16-byte all-reduce instead).
 """
 import ctypes as C
 
@@ -30,7 +32,7 @@ class ShardedPVGO:
     """One graph sharded over `world` ranks (world a power of two).  Collectives go through `group`; with the gloo
     backend (CPU test rigs) the buffers are staged through host memory."""
 
-    def __init__(self, N, links, device, rank=None, world=None, group=None):
+    def __init__(self, N, links, device, rank=None, world=None, group=None, exchange='p2p'):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -52,6 +54,18 @@ class ShardedPVGO:
         self._mine_pose = torch.as_tensor(pose_owner == self.rank, device=self.s.device)
         self._mine_vel = torch.as_tensor(vel_owner == self.rank, device=self.s.device)
         self._nccl = dist.get_backend(group) == 'nccl'
+        if exchange not in ('p2p', 'nccl'):
+            raise IslamError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
+        if exchange == 'p2p':
+            # every rank exports the CUDA IPC handle of its mailbox; the table of all handles goes back into the library
+            buf = (C.c_ubyte * 64)()
+            _lib.check(L.islam_pvgo_mailbox_export(h, buf), 'islam_pvgo_mailbox_export')
+            mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.s.device if self._nccl else 'cpu')
+            table = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(table, mine, group=group)
+            raw = torch.stack(table).cpu().numpy().tobytes()
+            _lib.check(L.islam_pvgo_mailbox_connect(h, raw), 'islam_pvgo_mailbox_connect')
 
     # passthroughs
     def set_problem(self, *a, **k):
@@ -78,7 +92,8 @@ class ShardedPVGO:
             _lib.check(s.L.islam_pvgo_lm_try_begin(s._h, st), 'islam_pvgo_lm_try_begin')
             self._allreduce(self.shared)
             _lib.check(s.L.islam_pvgo_lm_try_mid(s._h, st), 'islam_pvgo_lm_try_mid')
-            self._allreduce(self.sums)
+            if self.exchange == 'nccl':
+                self._allreduce(self.sums)
             _lib.check(s.L.islam_pvgo_lm_try_end(s._h, st), 'islam_pvgo_lm_try_end')
 
     def lm_run(self, budget=None):

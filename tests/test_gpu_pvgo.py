@@ -113,7 +113,7 @@ def test_window_with_scheduler_matches_oracle():
     assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= 1e-5
 
 
-def _mg_worker(rank, world, port, out):
+def _mg_worker(rank, world, port, out, exchange):
     import os
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -122,7 +122,7 @@ def _mg_worker(rank, world, port, out):
     dist.init_process_group('nccl', device_id=dev)
     from islam_b200.dist import ShardedPVGO
     g = synth.config2(N=600, band=8)
-    sh = ShardedPVGO(g.N, g.links, dev)
+    sh = ShardedPVGO(g.N, g.links, dev, exchange=exchange)
     sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
     sh.set_state(g.init_nodes, g.init_vels)
     sh.lm_reset(radius=g.radius, max_steps=5, use_scheduler=0)
@@ -133,14 +133,16 @@ def _mg_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 4])
-def test_sharded_lm_matches_single_gpu_and_oracle(world, tmp_path):
-    """contiguous pose windows + one all-reduce of separator panels per try; identical decisions on all ranks."""
+@pytest.mark.parametrize('world,exchange', [(2, 'p2p'), (2, 'nccl'), (4, 'p2p')])
+def test_sharded_lm_matches_single_gpu_and_oracle(world, exchange, tmp_path):
+    """contiguous pose windows + one all-reduce of separator panels per try; identical decisions on all ranks.
+    exchange='p2p': the trial sums travel through NVLink peer mailboxes inside the kernel that closes the try (no second
+    collective); 'nccl': a 16-byte all-reduce instead."""
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
     import torch.multiprocessing as mp
     out = str(tmp_path / 'mg.pt')
-    mp.spawn(_mg_worker, args=(world, 29533 + world, out), nprocs=world, join=True)
+    mp.spawn(_mg_worker, args=(world, 29533 + world + (7 if exchange == 'nccl' else 0), out, exchange), nprocs=world, join=True)
     r = torch.load(out)
     g = synth.config2(N=600, band=8)
     s = _solver(g)

@@ -10,8 +10,8 @@ rank, world, lr = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os
 torch.cuda.set_device(lr)
 dev = torch.device('cuda', lr)
 dist.init_process_group('nccl', device_id=dev)
-for name, g, steps in (('band8_600', synth.config2(N=600, band=8), 5), ('C2', synth.config2(), 10)):
-    sh = ShardedPVGO(g.N, g.links, dev)
+for name, g, steps, ex in (('band8_600', synth.config2(N=600, band=8), 5, 'p2p'), ('C2', synth.config2(), 10, 'nccl'), ('C2', synth.config2(), 10, 'p2p')):
+    sh = ShardedPVGO(g.N, g.links, dev, exchange=ex)
     sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
     for rep in range(3):
         sh.set_state(g.init_nodes, g.init_vels)
@@ -30,7 +30,7 @@ for name, g, steps in (('band8_600', synth.config2(N=600, band=8), 5), ('C2', sy
         st1 = s1.lm_run()
         n1, v1 = s1.get_state()
         d = (n - n1).abs().max().item()
-        print(f'[{name}] world={world} shared_fronts={sh.s.dims.n_shared_fronts} shared_MB={sh.s.dims.shared_doubles*8/1e6:.2f} '
+        print(f'[{name}] exchange={ex} world={world} shared_fronts={sh.s.dims.n_shared_fronts} shared_MB={sh.s.dims.shared_doubles*8/1e6:.2f} '
               f'steps={st.steps_done} tries={st.tries_total} loss={st.loss:.9f} (1-GPU {st1.loss:.9f}) '
               f'max|nodes-nodes_1gpu|={d:.3e} ms/try={1e3*dt/max(1,st.tries_total):.3f}', flush=True)
         from oracle import pvgo_oracle as po
