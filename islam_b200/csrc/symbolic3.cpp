@@ -38,6 +38,30 @@ struct Builder3 {
     // nested dissection of a sorted variable list; `nparts` pose windows (multi-GPU) starting at `part0` live inside it
     void recurse(std::vector<int>&& vars, int part0, int nparts) {
         if (vars.empty()) return;
+        // disconnected pieces (the chain is cut wherever a whole pose was promoted to the root) are independent subtrees:
+        // no separator between them
+        if (nparts <= 1 && (int)vars.size() > leaf_vars) {
+            const int id = ++calls;
+            for (int v : vars) { stamp[v] = id; side[v] = 0; }
+            std::vector<std::vector<int>> comps;
+            std::vector<int> stack;
+            for (int v0 : vars) {
+                if (side[v0]) continue;
+                comps.emplace_back();
+                side[v0] = 1; stack.push_back(v0);
+                while (!stack.empty()) {
+                    int v = stack.back(); stack.pop_back();
+                    comps.back().push_back(v);
+                    for (int q : adj[v])
+                        if (stamp[q] == id && !side[q]) { side[q] = 1; stack.push_back(q); }
+                }
+            }
+            if (comps.size() > 1) {
+                std::vector<int>().swap(vars);
+                for (auto& c : comps) { std::sort(c.begin(), c.end()); recurse(std::move(c), part0, 1); }
+                return;
+            }
+        }
         // the cut is placed among the poses that still have a tau / phi variable here: velocity-only tails (left over
         // from an earlier trim) hang off the chain and must not skew the balance of the tree
         int pmin = -1, pmax = -1;
@@ -100,6 +124,21 @@ int build_plan3(const Plan& base, const int64_t* links, const SymbolicOpts& opts
         long long a = links[2 * e], b = links[2 * e + 1];
         if (std::llabs(a - b) > opts.band_max)
             for (int c = 0; c < 2; ++c) { is_root[3 * a + c] = 1; is_root[3 * b + c] = 1; }
+    }
+
+    // With a dense root (many closures) the chain below it must stay shallow and narrow: every `cut_every`-th closure
+    // pose also gives its velocity to the root, which CUTS the chain there (nothing couples across a fully promoted
+    // pose).  The pieces in between become independent subtrees whose fronts only see their own few closure poses,
+    // instead of a 13-level tree whose top separators see thousands of root variables.
+    {
+        int n_root_poses = 0;
+        for (int i = 0; i < N; ++i) n_root_poses += is_root[3 * i];
+        if (n_root_poses >= opts.dense_root_min) {
+            const int cut_every = 8;
+            int k = 0;
+            for (int i = 0; i < N; ++i)
+                if (is_root[3 * i] && (k++ % cut_every) == 0) is_root[3 * i + 2] = 1;
+        }
     }
 
     // ---- ordering ---------------------------------------------------------------------------------------------
