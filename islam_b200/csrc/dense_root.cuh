@@ -128,54 +128,92 @@ k_root_trsm(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int fo
         for (int c = 0; c < nbk; ++c) rv.R[row + (size_t)(k0 + c) * rv.ld] = X[c * 128 + tid];
 }
 
-// trailing update C -= A_i A_j^T over 64x64 tiles of the lower triangle (rows up to and including the rhs row)
+// trailing update C -= A_i A_j^T over 128x128 tiles of the lower triangle (rows up to and including the rhs row) on the
+// FP64 tensor cores: mma.sync m8n8k4 (DMMA).  This is the one genuinely dense contraction of the path (north_star: "tensor
+// cores only on the dense Schur-complement GEMM"); on B200 the DMMA path has the same peak as the DFMA pipe, but a warp
+// instruction carries 256 multiply-adds, so the kernel is no longer bound by shared-memory operand traffic the way the 4x4
+// register-tile SIMT version was.  8 warps per CTA, warp tile 32 x 64 = 4 x 8 MMA tiles, both operand panels (k <= 64) staged
+// once in shared memory as [k][row] with a row stride of 136 doubles (conflict-free fragment loads).
+constexpr int SY_T = 128, SY_LD = SY_T + 8;
+constexpr size_t SY_SMEM = sizeof(double) * 2 * DR_NB * SY_LD;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(256)
 k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force) {
     if (!force && !st->active) return;
     extern __shared__ __align__(16) double sm_syrk[];
-    double (*As)[DR_NB] = reinterpret_cast<double (*)[DR_NB]>(sm_syrk);                    // [k][row]
-    double (*Bs)[DR_NB] = reinterpret_cast<double (*)[DR_NB]>(sm_syrk + DR_NB * DR_NB);
+    double* As = sm_syrk;                      // [k][row], row stride SY_LD
+    double* Bs = sm_syrk + DR_NB * SY_LD;
     const int t = blockIdx.x;
     int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((long long)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
     while ((long long)ti * (ti + 1) / 2 > t) --ti;
     const int tj = t - (int)((long long)ti * (ti + 1) / 2);
     const int base = k0 + nbk;
-    const int r0 = base + 64 * ti, c0 = base + 64 * tj;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < 64 * nbk; idx += 256) {
-        int k = idx >> 6, r = idx & 63;
-        As[k][r] = (r0 + r <= rv.n) ? rv.R[(r0 + r) + (size_t)(k0 + k) * rv.ld] : 0.0;
-        Bs[k][r] = (c0 + r < rv.n) ? rv.R[(c0 + r) + (size_t)(k0 + k) * rv.ld] : 0.0;
+    const int r0 = base + SY_T * ti, c0 = base + SY_T * tj;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nbk4 = (nbk + 3) & ~3;
+    // operand panels: asynchronous 8-byte copies global -> shared (no register staging, all of them in flight at once);
+    // out-of-range rows / the k padding are zero-filled (src-size 0)
+    for (int idx = tid; idx < SY_T * nbk4; idx += 256) {
+        const int k = idx >> 7, r = idx & (SY_T - 1);
+        const bool va = k < nbk && r0 + r <= rv.n, vb = k < nbk && c0 + r < rv.n;
+        const double* ga = rv.R + (va ? (size_t)(r0 + r) + (size_t)(k0 + k) * rv.ld : 0);
+        const double* gb = rv.R + (vb ? (size_t)(c0 + r) + (size_t)(k0 + k) * rv.ld : 0);
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(As + k * SY_LD + r);
+        const unsigned sb = (unsigned)__cvta_generic_to_shared(Bs + k * SY_LD + r);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(ga), "r"(va ? 8 : 0));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sb), "l"(gb), "r"(vb ? 8 : 0));
     }
+    asm volatile("cp.async.commit_group;");
+    const int wr = 32 * (w & 3), wc = 64 * (w >> 2);       // this warp's 32 x 64 piece of the tile
+    const bool idle = ti == tj && wr + 31 < wc;             // entirely above the diagonal
+    const int lk = lane & 3, lm = lane >> 2;
+    // the accumulators start as the C tile itself (its loads overlap the panel copies) and the A fragments are negated:
+    // D = (-A) B + C, so the result is stored without a dependent read-modify-write at the end
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + wr + 8 * i + lm;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = c0 + wc + 8 * j + 2 * lk + e;
+                acc[i][j][e] = (!idle && r <= rv.n && c < rv.n && r >= c) ? rv.R[r + (size_t)c * rv.ld] : 0.0;
+            }
+    }
+    asm volatile("cp.async.wait_group 0;");
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;              // rows 4*tx.., cols 4*ty..
-    double acc[4][4];
+    if (idle) return;
+    for (int k4 = 0; k4 < nbk4; k4 += 4) {
+        const double* ap = As + (k4 + lk) * SY_LD + wr + lm;
+        const double* bp = Bs + (k4 + lk) * SY_LD + wc + lm;
+        double a[4], b[8];
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+        for (int i = 0; i < 4; ++i) a[i] = -ap[8 * i];
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < nbk; ++k) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&As[k][4 * tx]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&As[k][4 * tx + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][4 * ty]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][4 * ty + 2]);
-        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int j = 0; j < 8; ++j) b[j] = bp[8 * j];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+            for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-        const int c = c0 + 4 * ty + y;
-        if (c >= rv.n) continue;
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + wr + 8 * i + lm;
+        if (r > rv.n) continue;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int r = r0 + 4 * tx + x;
-            if (r <= rv.n && r >= c) rv.R[r + (size_t)c * rv.ld] -= acc[x][y];
-        }
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = c0 + wc + 8 * j + 2 * lk + e;
+                if (c < rv.n && r >= c) rv.R[r + (size_t)c * rv.ld] = acc[i][j][e];
+            }
     }
 }
 

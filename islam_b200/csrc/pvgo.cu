@@ -447,7 +447,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         rv.vars = h->d_root_vars.p; rv.children = h->d_root_children.p; rv.nchildren = (int)kids.size();
         h->has_root = true;
         cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128)));
-        cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * DR_NB * DR_NB));
+        cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
     }
     // LM state
     LMState s;
@@ -605,9 +605,9 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
         if (below > 0)
             k_root_trsm<<<(below + 127) / 128, 128, sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128), s>>>(h->st.p, rv, k0, nbk, force);
         if (k0 + nbk < rv.n) {
-            long long T = (below + 63) / 64;
+            long long T = (below + SY_T - 1) / SY_T;
             long long ntiles = T * (T + 1) / 2;
-            k_root_syrk<<<(unsigned)ntiles, 256, sizeof(double) * 2 * DR_NB * DR_NB, s>>>(h->st.p, rv, k0, nbk, force);
+            k_root_syrk<<<(unsigned)ntiles, 256, SY_SMEM, s>>>(h->st.p, rv, k0, nbk, force);
         }
     }
     return (int)cudaGetLastError();
