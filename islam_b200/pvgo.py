@@ -13,8 +13,6 @@ The reference builds a dense PyPose LM problem per call; here the graph structur
 cached, the information matrices collapse to the four scalars they are made of (pvgo.py:125-129), and the whole
 `while scheduler.continual()` loop (pvgo.py:177-180) runs on the device.  There is no CPU path.
 """
-import hashlib
-
 import numpy as np
 import torch
 
@@ -48,8 +46,13 @@ def get_solver(N, links, device):
     dev = torch.device(device)
     if dev.type == 'cuda' and dev.index is None:
         dev = torch.device('cuda', torch.cuda.current_device())
-    key = (int(N), str(dev), hashlib.blake2b(links_np.tobytes(), digest_size=16).hexdigest())
+    # cheap structural key (two vectorised checksums), confirmed by an exact comparison with the cached edge list:
+    # a cryptographic hash of the edge list cost ~0.6 ms per run_pvgo call at 40 000 edges
+    flat = links_np.reshape(-1)
+    key = (int(N), str(dev), links_np.shape[0], int(flat.sum()), int(flat[::3].sum()), int(flat[1::5].sum()))
     s = _SOLVER_CACHE.get(key)
+    if s is not None and not np.array_equal(s.links, links_np):
+        s = None
     if s is None:
         if len(_SOLVER_CACHE) >= _CACHE_MAX:
             _SOLVER_CACHE.pop(next(iter(_SOLVER_CACHE)))
