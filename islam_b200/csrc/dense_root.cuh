@@ -12,6 +12,7 @@
 // library: a closure pose collects contributions from both chain neighbours and every closure it takes part in).
 #pragma once
 #include "common.cuh"
+#include "solver3.cuh"
 
 namespace islam {
 
@@ -62,7 +63,7 @@ k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int cc = warp; cc < ub - 1; cc += 8) {
         const int pc = 3 * cm[cc / 3] + cc % 3;
-        const double* col = U + ((size_t)cc * ub - (size_t)cc * (cc - 1) / 2 - cc);
+        const double* col = U + f3_ucol(cc, ub);
         for (int r = cc + lane; r < ub; r += 32) {
             const int pr = (r == ub - 1) ? rv.n : 3 * cm[r / 3] + r % 3;
             atomicAdd(&rv.R[pr + (size_t)pc * rv.ld], col[r]);

@@ -392,12 +392,12 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         std::vector<unsigned short> dmap((size_t)q.U_doubles, 0xFFFF);
         for (int f = 0; f < q.F; ++f) {
             if (f == q.dense_root || (h->level_variant[q.f_level[f]] & 3) != 2) continue;
-            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub, ld = f3_ld(Rf), uoff = ld * Cf + 4;
+            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub, ld = f3_ld(Rf), uoff = ld * Cf + F3_PAD;
             for (int k = q.f_child_off[f]; k < q.f_child_off[f + 1]; ++k) {
                 const int c = q.f_children[k], ubc = 3 * q.f_nb[c] + 1;
                 const int* cm = &q.c_map[q.c_map_off[k]];
                 unsigned short* dm = dmap.data() + q.f_Uoff[c];
-                for (int cc = 0; cc < ubc - 1; ++cc) {
+                for (int cc = 0; cc < ubc - 1; ++cc) {                      // the (rhs, rhs) corner stays unmapped
                     const int pc = 3 * cm[cc / 3] + cc % 3;
                     for (int r = cc; r < ubc; ++r) {
                         const int pr = (r == ubc - 1) ? Rf - 1 : 3 * cm[r / 3] + r % 3;

@@ -35,14 +35,24 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 constexpr int F3_HEAD = 192 + 128;   // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
                                       // diagonal), then 256 ints of staged child maps
 constexpr int F3_CMAP_INTS = 256;
+constexpr int F3_PAD = 8;            // zeroed doubles behind the panel: operand loads of edge tiles may run past its last column
 constexpr int F3_PRE = 8;            // original entries per thread whose maps are resolved before the grid dependency
 
 __host__ __device__ __forceinline__ int f3_ld(int Rf) { return (Rf + 3) & ~3; }      // 32-byte aligned columns
-__host__ __device__ __forceinline__ long long f3_ulen(int ub) { return (long long)ub * (ub + 1) / 2; }
-// packed lower triangle, column-major: element (r, c), r >= c
-__host__ __device__ __forceinline__ int f3_uidx(int r, int c, int ub) { return c * ub - c * (c - 1) / 2 + (r - c); }
+// Update matrix U ((3nb+1)^2, lower triangle + rhs row): columns are stored in PAIRS (2j, 2j+1), both from row 2j down to
+// row ube-1 (ube = ub rounded up to even).  Every column therefore starts at an even offset relative to an even row, so a
+// pair of rows (2i, 2i+1) of any column is one aligned 16-byte access: conflict-free vector read-modify-write in the
+// Schur update.  ~3 % larger than the tight packing; the extra slots ((2j, 2j+1) and the pad row) are never read.
+__host__ __device__ __forceinline__ int f3_ube(int ub) { return (ub + 1) & ~1; }
+__host__ __device__ __forceinline__ long long f3_ulen(int ub) { const long long e = f3_ube(ub); return e * (e / 2 + 1); }
+// element (r, c), r >= c, sits at f3_ucol(c, ub) + r
+__host__ __device__ __forceinline__ int f3_ucol(int c, int ub) {
+    const int e = f3_ube(ub), j = c >> 1;
+    return 2 * j * (e - j + 1) + (c & 1) * (e - 2 * j) - 2 * j;
+}
+__host__ __device__ __forceinline__ int f3_uidx(int r, int c, int ub) { return f3_ucol(c, ub) + r; }
 __host__ __device__ __forceinline__ long long f3_smem_doubles(int Rf, int Cf, int ub, int mode) {
-    return F3_HEAD + (mode >= 1 ? (long long)f3_ld(Rf) * Cf + 4 : 0) + (mode == 2 ? f3_ulen(ub) : 0);
+    return F3_HEAD + (mode >= 1 ? (long long)f3_ld(Rf) * Cf + F3_PAD : 0) + (mode == 2 ? f3_ulen(ub) : 0);
 }
 
 // ---- numeric factorisation of one level ------------------------------------------------------------------------------
@@ -81,12 +91,12 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
     double* P = P_SMEM ? smem + F3_HEAD : Lg;
-    double* Uw = U_SMEM ? P + ld * Cf + 4 : Ug;
+    double* Uw = U_SMEM ? P + ld * Cf + F3_PAD : Ug;
     const int* vars = m.vars + m.vars_off[f];
     const int k0 = m.child_off[f], nch = m.child_off[f + 1] - k0;
     const int o0 = m.orig_off[f], no = m.orig_off[f + 1] - o0;
     if (P_SMEM)
-        for (int i = tid; i < ld * Cf + 4; i += NT) P[i] = 0.0;
+        for (int i = tid; i < ld * Cf + F3_PAD; i += NT) P[i] = 0.0;
     if (U_SMEM)
         for (int i = tid; i < ulen; i += NT) Uw[i] = 0.0;
     // resolve this thread's first F3_PRE original entries (immutable maps -> source offset, destination) and stage the
@@ -203,7 +213,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
                 // destinations precomputed on the host (offsets into [P | U] in shared memory, same packed order as the
                 // child's U): two coalesced streams, eight independent element pairs in flight per thread
                 const unsigned short* dm = m.dmap + m.Uoff[c];
-                const int n = (int)f3_ulen(ubc) - 1;                   // the last element is the unused (rhs, rhs) corner
+                const int n = (int)f3_ulen(ubc);                       // unused slots of the layout carry 0xFFFF
                 for (int e0 = tid; e0 < n; e0 += 8 * NT) {
                     double v[8];
                     int d[8];
@@ -211,11 +221,11 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
                     for (int u = 0; u < 8; ++u) {
                         const int e = e0 + u * NT;
                         v[u] = e < n ? Uc[e] : 0.0;
-                        d[u] = e < n ? (int)dm[e] : -1;
+                        d[u] = e < n ? (int)dm[e] : 0xFFFF;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        if (d[u] >= 0) P[d[u]] += v[u];
+                        if (d[u] != 0xFFFF) P[d[u]] += v[u];
                 }
             } else
             for (int cc0 = 4 * warp; cc0 < ubc - 1; cc0 += 4 * NW) {   // the last column is the unused (rhs, rhs) corner
@@ -224,7 +234,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int cc = cc0 + j;
-                        const double* col = Uc + ((size_t)cc * ubc - (size_t)cc * (cc - 1) / 2 - cc);
+                        const double* col = Uc + f3_ucol(cc < ubc ? cc : 0, ubc);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int r = cc + r0 + lane + 32 * u;
@@ -328,67 +338,68 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             Lg[i + (size_t)(c0 + q) * Rf] = P[i + (c0 + q) * ld];
         }
     };
-    // U -= L21[:, blocks] L21[:, blocks]^T over the lower triangle (+ rhs row), 4x4 register tiles.  Tiles are laid
-    // out on ABSOLUTE panel rows from R0 = Cf rounded down to even, so the LDS.128 operand pairs are 16-byte aligned
-    // whatever the parity of Cf (a tile row above Cf is computed and dropped).
-    const int R0 = Cf & ~1, shift = Cf - R0;
-    const int ntr = (ub + shift + 3) >> 2, ntiles = ub > 1 ? ntr * (ntr + 1) / 2 : 0;
-    auto tile_of = [&](int t, int& tr, int& tc) {
-        tr = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
-        while (tr * (tr + 1) / 2 > t) --tr;
-        tc = t - tr * (tr + 1) / 2;
+    // U -= L21[:, blocks] L21[:, blocks]^T over the lower triangle (+ rhs row).  Register tiles of 2 rows x 8 columns with
+    // the lanes of a warp along the ROWS: the row operand is one 16-byte load per lane, contiguous across the warp, the
+    // eight column operands are four broadcast loads, and the read-modify-write of U is one aligned 16-byte access per
+    // column (paired-column layout above) — no bank-conflict replays anywhere.  Tiles are enumerated column block by
+    // column block: block tc covers columns [8 tc, 8 tc + 8) and the row pairs from 4 tc on.
+    const int npair = f3_ube(ub) >> 1, ncblk = (ub + 7) >> 3;
+    auto tiles_before = [&](int tc) { return tc * npair - 2 * tc * (tc - 1); };    // sum_{j<tc} (npair - 4 j)
+    const int ntiles = ub > 1 ? tiles_before(ncblk) : 0;
+    auto tile_of = [&](int t, int& tp, int& tc) {
+        tc = 0;
+        while (tc + 1 < ncblk && tiles_before(tc + 1) <= t) ++tc;
+        tp = 4 * tc + (t - tiles_before(tc));
     };
-    int tr_first = 0, tc_first = 0;            // the first tile of this thread in the shadowed steps (threads 32..NT-1)
-    if (tid >= 32 && tid - 32 < ntiles) tile_of(tid - 32, tr_first, tc_first);
+    int tp_first = 0, tc_first = 0;            // the first tile of this thread in the shadowed steps (threads 32..NT-1)
+    if (tid >= 32 && tid - 32 < ntiles) tile_of(tid - 32, tp_first, tc_first);
+    const bool cf_even = (Cf & 1) == 0;        // panel rows Cf + 2 tp are 16-byte aligned (always so for P in shared memory)
     auto schur_blocks = [&](int jb0, int jb1, int t0, int nt) {     // block columns [jb0, jb1)
         const int c0 = 9 * jb0, kn = 9 * (jb1 - jb0);
         if (kn <= 0) return;
         for (int t = t0; t < ntiles; t += nt) {
-            int tr, tc;
-            if (t == tid - 32) { tr = tr_first; tc = tc_first; }
-            else tile_of(t, tr, tc);
-            const int r0 = 4 * tr, s0 = 4 * tc;
-            double acc[4][4];
+            int tp, tc;
+            if (t == tid - 32) { tp = tp_first; tc = tc_first; }
+            else tile_of(t, tp, tc);
+            const int r0 = 2 * tp, s0 = 8 * tc;
+            double acc[2][8];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-            const double* pa = P + R0 + r0 + c0 * ld;
-            const double* pb = P + R0 + s0 + c0 * ld;
+            for (int y = 0; y < 8; ++y) { acc[0][y] = 0.0; acc[1][y] = 0.0; }
+            const double* pa = P + Cf + r0 + c0 * ld;
+            const double* pb = P + Cf + s0 + c0 * ld;
+            if (P_SMEM && cf_even) {
 #pragma unroll 3
-            for (int k = 0; k < kn; ++k) {
-                double av[4], bv[4];
-                if (P_SMEM) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(pa + k * ld);
-                    const double2 a23 = *reinterpret_cast<const double2*>(pa + k * ld + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(pb + k * ld);
-                    const double2 b23 = *reinterpret_cast<const double2*>(pb + k * ld + 2);
-                    av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
-                    bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
-                } else {
+                for (int k = 0; k < kn; ++k) {
+                    const double2 a = *reinterpret_cast<const double2*>(pa + k * ld);
+                    double2 b[4];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        av[x] = (R0 + r0 + x < Rf) ? pa[k * ld + x] : 0.0;
-                        bv[x] = (R0 + s0 + x < Rf) ? pb[k * ld + x] : 0.0;
+                    for (int y = 0; y < 4; ++y) b[y] = *reinterpret_cast<const double2*>(pb + k * ld + 2 * y);
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        acc[0][2 * y] += a.x * b[y].x; acc[0][2 * y + 1] += a.x * b[y].y;
+                        acc[1][2 * y] += a.y * b[y].x; acc[1][2 * y + 1] += a.y * b[y].y;
                     }
                 }
+            } else {
+                // odd pivot width or panel in global memory: scalar operand loads (rows past the panel read as zero)
+#pragma unroll 3
+                for (int k = 0; k < kn; ++k) {
+                    const double a0 = pa[k * ld], a1 = (Cf + r0 + 1 < Rf) ? pa[k * ld + 1] : 0.0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+                    for (int y = 0; y < 8; ++y) {
+                        const double b = (Cf + s0 + y < Rf) ? pb[k * ld + y] : 0.0;
+                        acc[0][y] += a0 * b; acc[1][y] += a1 * b;
+                    }
+                }
             }
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int r = r0 + x - shift, s_ = s0 + y - shift;
-                    if (r >= 0 && s_ >= 0 && r < ub && s_ < ub && r >= s_ && !(r == ub - 1 && s_ == ub - 1)) {
-                        const int ui = f3_uidx(r, s_, ub);
-                        if (u_direct) Uw[ui] = -acc[x][y];
-                        else Uw[ui] -= acc[x][y];
-                    }
-                }
+            for (int y = 0; y < 8; ++y) {
+                const int s_ = s0 + y;
+                if (s_ >= ub || r0 + 1 < s_) continue;                 // the pair (r0, r0+1) lies above column s_
+                double2* up = reinterpret_cast<double2*>(Uw + f3_ucol(s_, ub) + r0);
+                if (u_direct) *up = make_double2(-acc[0][y], -acc[1][y]);
+                else { double2 u = *up; u.x -= acc[0][y]; u.y -= acc[1][y]; *up = u; }
+            }
         }
     };
     int pend_first = 0;                        // first finished block column not yet applied to U
