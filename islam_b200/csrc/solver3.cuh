@@ -200,8 +200,40 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     // A2. extend-add of the children's update matrices: a warp takes four columns of the child's packed lower triangle
     // at a time (up to sixteen independent coalesced loads in flight per lane); children one after the other (fixed order)
     {
-        int cm_off = 0;
-        for (int k = 0; k < nch; ++k) {
+        int cm_off = 0, kdone = 0;
+        if (MODE == 2 && m.dmap != nullptr && stage == 0) {
+            // fast path, children in pairs: the loads of BOTH update matrices (values + host-computed destinations, two
+            // coalesced streams each, up to 12 elements per thread) are in flight together, so the pair costs one memory
+            // latency; the additions still happen child after child (fixed summation order)
+            constexpr int CH = 12;
+            for (; kdone + 1 < nch; kdone += 2) {
+                const int cA = m.children[k0 + kdone], cB = m.children[k0 + kdone + 1];
+                const int nA = (int)f3_ulen(3 * m.nb[cA] + 1), nB = (int)f3_ulen(3 * m.nb[cB] + 1);
+                if (nA > CH * NT || nB > CH * NT) break;
+                const double* UA = Ubuf + m.Uoff[cA];
+                const double* UB = Ubuf + m.Uoff[cB];
+                const unsigned short* dA = m.dmap + m.Uoff[cA];
+                const unsigned short* dB = m.dmap + m.Uoff[cB];
+                double va[CH], vb[CH];
+                int da[CH], db[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int e = tid + u * NT;
+                    va[u] = e < nA ? UA[e] : 0.0; da[u] = e < nA ? (int)dA[e] : 0xFFFF;
+                    vb[u] = e < nB ? UB[e] : 0.0; db[u] = e < nB ? (int)dB[e] : 0xFFFF;
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u)
+                    if (da[u] != 0xFFFF) P[da[u]] += va[u];
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < CH; ++u)
+                    if (db[u] != 0xFFFF) P[db[u]] += vb[u];
+                __syncthreads();
+                cm_off += m.nb[cA] + m.nb[cB];
+            }
+        }
+        for (int k = kdone; k < nch; ++k) {
             const int c = m.children[k0 + k];
             const int nbc = m.nb[c], ubc = 3 * nbc + 1;
             const int* cm = cm_staged ? scm + cm_off : m.cmap + m.cmap_off[k0 + k];
