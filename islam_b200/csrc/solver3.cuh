@@ -32,9 +32,10 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 #define FRONT_T(k, f) do { } while (0)
 #endif
 
-constexpr int F3_HEAD = 192 + 128;   // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
-                                      // diagonal), then 256 ints of staged child maps
-constexpr int F3_CMAP_INTS = 256;
+constexpr int F3_HEAD = 192 + 64;    // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
+                                      // diagonal), then 128 ints of staged child maps.  Every byte counts here: a C2
+                                      // separator front is 115 328 bytes, and two of them must fit one SM (233 472)
+constexpr int F3_CMAP_INTS = 128;
 constexpr int F3_PAD = 8;            // zeroed doubles behind the panel: operand loads of edge tiles may run past its last column
 constexpr int F3_PRE = 8;            // original entries per thread whose maps are resolved before the grid dependency
 
