@@ -392,7 +392,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         std::vector<unsigned short> dmap((size_t)q.U_doubles, 0xFFFF);
         for (int f = 0; f < q.F; ++f) {
             if (f == q.dense_root || (h->level_variant[q.f_level[f]] & 3) != 2) continue;
-            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub, ld = f3_ld(Rf), uoff = ld * Cf + F3_PAD;
+            const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub, ld = f3_ld(Rf), uoff = ld * Cf + F3_PAD - (Cf & 1);   // relative to P (solver3.cuh)
             for (int k = q.f_child_off[f]; k < q.f_child_off[f + 1]; ++k) {
                 const int c = q.f_children[k], ubc = 3 * q.f_nb[c] + 1;
                 const int* cm = &q.c_map[q.c_map_off[k]];

@@ -91,13 +91,14 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     const int ulen = (int)f3_ulen(ub);
     double* Lg = Lbuf + m.Loff[f];
     double* Ug = Ubuf + m.Uoff[f];
-    double* P = P_SMEM ? smem + F3_HEAD : Lg;
-    double* Uw = U_SMEM ? P + ld * Cf + F3_PAD : Ug;
+    // the panel starts one double later when Cf is odd, so that the boundary rows (Cf + even) are 16-byte aligned
+    double* P = P_SMEM ? smem + F3_HEAD + (Cf & 1) : Lg;
+    double* Uw = U_SMEM ? smem + F3_HEAD + ld * Cf + F3_PAD : Ug;
     const int* vars = m.vars + m.vars_off[f];
     const int k0 = m.child_off[f], nch = m.child_off[f + 1] - k0;
     const int o0 = m.orig_off[f], no = m.orig_off[f + 1] - o0;
     if (P_SMEM)
-        for (int i = tid; i < ld * Cf + F3_PAD; i += NT) P[i] = 0.0;
+        for (int i = tid; i < ld * Cf + F3_PAD; i += NT) smem[F3_HEAD + i] = 0.0;
     if (U_SMEM)
         for (int i = tid; i < ulen; i += NT) Uw[i] = 0.0;
     // resolve this thread's first F3_PRE original entries (immutable maps -> source offset, destination) and stage the
@@ -386,7 +387,6 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     };
     int tp_first = 0, tc_first = 0;            // the first tile of this thread in the shadowed steps (threads 32..NT-1)
     if (tid >= 32 && tid - 32 < ntiles) tile_of(tid - 32, tp_first, tc_first);
-    const bool cf_even = (Cf & 1) == 0;        // panel rows Cf + 2 tp are 16-byte aligned (always so for P in shared memory)
     auto schur_blocks = [&](int jb0, int jb1, int t0, int nt) {     // block columns [jb0, jb1)
         const int c0 = 9 * jb0, kn = 9 * (jb1 - jb0);
         if (kn <= 0) return;
@@ -400,7 +400,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             for (int y = 0; y < 8; ++y) { acc[0][y] = 0.0; acc[1][y] = 0.0; }
             const double* pa = P + Cf + r0 + c0 * ld;
             const double* pb = P + Cf + s0 + c0 * ld;
-            if (P_SMEM && cf_even) {
+            if (P_SMEM) {
 #pragma unroll 3
                 for (int k = 0; k < kn; ++k) {
                     const double2 a = *reinterpret_cast<const double2*>(pa + k * ld);
@@ -414,7 +414,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
                     }
                 }
             } else {
-                // odd pivot width or panel in global memory: scalar operand loads (rows past the panel read as zero)
+                // panel in global memory: scalar operand loads (rows past the panel read as zero)
 #pragma unroll 3
                 for (int k = 0; k < kn; ++k) {
                     const double a0 = pa[k * ld], a1 = (Cf + r0 + 1 < Rf) ? pa[k * ld + 1] : 0.0;
