@@ -19,6 +19,7 @@ struct Front3Meta {
     const long long* Loff;  // [F] offset of the (3(npad+nb)+1) x 3npad column-major panel
     const long long* Uoff;  // [F] offset of the packed lower triangle of the (3nb+1)^2 update matrix
     const long long* Ioff;  // [F] offset of the npad/3 inverse 9x9 diagonal blocks
+    const int* parent;      // [F] parent front or -1
     const int* child_off;   // [F+1]
     const int* children;    // child front ids
     const int* cmap_off;    // [nchildren_total+1]

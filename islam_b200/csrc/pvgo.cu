@@ -168,7 +168,8 @@ struct islam_pvgo {
     // symbolic plan on the device
     DevBuf<int> d_node_eoff, d_node_edges, d_pair_lo, d_pair_hi, d_pair_adj, d_pair_eoff, d_pair_edges;
     DevBuf<int> d_np, d_npad, d_nb, d_vars_off, d_vars, d_child_off, d_children, d_cmap_off, d_cmap, d_orig_off, d_orig_rs,
-        d_orig_cs, d_orig_src, d_part, d_level_fronts, d_shared_fronts, d_root_vars, d_root_children;
+        d_orig_cs, d_orig_src, d_part, d_level_fronts, d_shared_fronts, d_root_vars, d_root_children, d_parent, d_bs_chain,
+        d_bs_count;
     DevBuf<long long> d_Loff, d_Uoff, d_Ioff, d_shared_off;
     DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
     DevBuf<unsigned short> d_dmap;
@@ -190,6 +191,8 @@ struct islam_pvgo {
     int n_sm = 148;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
     std::vector<int> level_nlocal, level_nshared;
+    // back-substitution: the levels [bs_chain_from, n_levels) run as ONE launch of bs_chain_n co-resident CTAs (parents first)
+    int bs_chain_from = 0, bs_chain_n = 0, bs_chain_late = 0, bs_chain_bytes = 0;
     std::vector<long long> h_shared_off;
     long long shared_doubles = 0;
     int n_shared = 0;
@@ -204,7 +207,8 @@ struct islam_pvgo {
         DevBuf<int>* ib[] = {&ei, &ej, &edge_owner, &pair_owner, &d_node_eoff, &d_node_edges, &d_pair_lo, &d_pair_hi,
                              &d_pair_adj, &d_pair_eoff, &d_pair_edges, &d_np, &d_npad, &d_nb, &d_vars_off, &d_vars,
                              &d_child_off, &d_children, &d_cmap_off, &d_cmap, &d_orig_off, &d_orig_rs, &d_orig_cs,
-                             &d_orig_src, &d_part, &d_level_fronts, &d_shared_fronts, &d_root_vars, &d_root_children};
+                             &d_orig_src, &d_part, &d_level_fronts, &d_shared_fronts, &d_root_vars, &d_root_children, &d_parent, &d_bs_chain,
+                             &d_bs_count};
         for (auto* b : ib) b->release();
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot};
@@ -299,7 +303,8 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     UP(d_np, q.f_np); UP(d_npad, q.f_npad); UP(d_nb, q.f_nb); UP(d_vars_off, q.f_vars_off); UP(d_vars, q.f_vars);
     UP(d_child_off, q.f_child_off); UP(d_children, q.f_children); UP(d_cmap_off, q.c_map_off); UP(d_cmap, q.c_map);
     UP(d_orig_off, q.f_orig_off); UP(d_orig_rs, q.orig_rs); UP(d_orig_cs, q.orig_cs); UP(d_orig_src, q.orig_src);
-    UP(d_part, q.f_part); UP(d_Loff, q.f_Loff); UP(d_Uoff, q.f_Uoff); UP(d_Ioff, q.f_Ioff);
+    UP(d_part, q.f_part); UP(d_Loff, q.f_Loff); UP(d_Uoff, q.f_Uoff); UP(d_Ioff, q.f_Ioff); UP(d_parent, q.f_parent);
+    { std::vector<int> zeros(q.F, 0); UP(d_bs_count, zeros); }
     // level lists: local fronts first, shared fronts last (multi-GPU: local = fronts of this rank's window)
     {
         std::vector<int> lf = q.level_fronts;
@@ -333,6 +338,25 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         h->n_shared = (int)shared_list.size();
         h->shared_doubles = off + 4;      // + [lin loss, trial loss, quality, spare]
         UP(d_level_fronts, lf);
+        // top of the tree for the chained back-substitution: as many levels as fit the SMs together, parents first
+        {
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            std::vector<int> chain;
+            int from = q.n_levels;
+            for (int l = q.n_levels - 1; l >= 0; --l) {
+                const int n = h->level_nlocal[l] + h->level_nshared[l];
+                if ((int)chain.size() + n > n_sm) break;
+                if (chain.empty()) h->bs_chain_late = n;
+                for (int k = 0; k < n; ++k) chain.push_back(lf[q.level_off[l] + k]);
+                from = l;
+            }
+            if (chain.empty()) h->bs_chain_late = 0;      // (a top level emptied by the dense root contributes no CTAs)
+            h->bs_chain_from = from;
+            h->bs_chain_n = (int)chain.size();
+            UP(d_bs_chain, chain);
+        }
         UP(d_shared_fronts, shared_list);
         UP(d_shared_off, h->h_shared_off);
         AL(shared, (size_t)h->shared_doubles);
@@ -385,6 +409,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             h->level_smem_bytes[l] = (int)bytes;
             h->level_bs_bytes[l] = (int)(bs_full[l] <= max_optin ? bs_full[l] : bs_min[l]);
         }
+        for (int l = h->bs_chain_from; l < q.n_levels; ++l) h->bs_chain_bytes = std::max(h->bs_chain_bytes, h->level_bs_bytes[l]);
     }
     // extend-add destination maps (solver3.cuh A2) for the parents whose whole frontal matrix sits in shared memory
     h->fm.dmap = nullptr;
@@ -429,7 +454,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     av.pair_edges = h->d_pair_edges.p; av.P = p.P;
     Front3Meta& fm = h->fm;
     fm.np = h->d_np.p; fm.npad = h->d_npad.p; fm.nb = h->d_nb.p; fm.vars_off = h->d_vars_off.p; fm.vars = h->d_vars.p;
-    fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.Ioff = h->d_Ioff.p; fm.child_off = h->d_child_off.p;
+    fm.Loff = h->d_Loff.p; fm.Uoff = h->d_Uoff.p; fm.Ioff = h->d_Ioff.p; fm.child_off = h->d_child_off.p; fm.parent = h->d_parent.p;
     fm.children = h->d_children.p; fm.cmap_off = h->d_cmap_off.p; fm.cmap = h->d_cmap.p; fm.orig_off = h->d_orig_off.p;
     fm.orig_rs = h->d_orig_rs.p; fm.orig_cs = h->d_orig_cs.p; fm.orig_src = h->d_orig_src.p;
     fm.part = h->d_part.p; fm.shared_off = h->d_shared_off.p; fm.mypart = opts.part;
@@ -640,13 +665,21 @@ static int launch_factor_shared(islam_pvgo* h, cudaStream_t s, double forced_sca
 static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan3& p = h->p3;
     { int rc = launch_root_solve(h, s, force); if (rc) return rc; }
-    int launched = 0;                          // pre_ok: the previous kernel in the stream is the parent level's back-substitution
-    for (int l = p.n_levels - 1; l >= 0; --l) {
+    // top of the tree: one launch, parents first, fronts chained through completion counters (solver3.cuh)
+    int first_separate = p.n_levels - 1;
+    if (h->bs_chain_n > 0) {
+        CK(launch_pdl(k_backsolve3, h->bs_chain_n, BS3_THREADS, (size_t)h->bs_chain_bytes, s, (const LMState*)h->st.p,
+                      (const int*)h->d_bs_chain.p, h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p, h->D.p, force,
+                      h->bs_chain_bytes / 8, h->bs_chain_late, 1, h->d_bs_count.p, p.dense_root));
+        first_separate = h->bs_chain_from - 1;
+    }
+    for (int l = first_separate; l >= 0; --l) {            // the wide levels below: one launch each
         int n = h->level_nlocal[l] + h->level_nshared[l];
         if (!n) continue;
+        const int n_late = (h->bs_chain_n == 0 && l == p.n_levels - 1) ? n : 0;
         CK(launch_pdl(k_backsolve3, n, BS3_THREADS, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
                       (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
-                      h->D.p, force, h->level_bs_bytes[l] / 8, launched++ > 0));
+                      h->D.p, force, h->level_bs_bytes[l] / 8, n_late, 0, h->d_bs_count.p, p.dense_root));
     }
     return (int)cudaGetLastError();
 }
@@ -1014,6 +1047,10 @@ extern "C" int islam_debug_phase_grid(int g) { return (int)cudaMemcpyToSymbol(is
 extern "C" int islam_debug_front_times(unsigned long long* out /* [4][8192] */) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, islam::g_front_t, sizeof(unsigned long long) * 4 * 8192);
+}
+extern "C" int islam_debug_bs_times(unsigned long long* out /* [4][8192] */) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, islam::g_bs_t, sizeof(unsigned long long) * 4 * 8192);
 }
 extern "C" int islam_debug_phase_clocks(long long* out64) {
     cudaDeviceSynchronize();

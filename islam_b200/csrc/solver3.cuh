@@ -24,12 +24,15 @@ __device__ int g_phase_grid = 1;
 #define PHASE(n) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
 // per front: globaltimer at CTA start, after the grid dependency, at the end; SM id  (tools/level_timeline.py)
 __device__ unsigned long long g_front_t[4][8192];
+__device__ unsigned long long g_bs_t[4][8192];
+#define BS_T(k, f) do { if (threadIdx.x == 0 && (f) < 8192) g_bs_t[k][f] = (k) == 3 ? (unsigned long long)smid() : gtime(); } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define FRONT_T(k, f) do { if (threadIdx.x == 0 && (f) < 8192) g_front_t[k][f] = (k) == 3 ? (unsigned long long)smid() : gtime(); } while (0)
 #else
 #define PHASE(n) do { } while (0)
 #define FRONT_T(k, f) do { } while (0)
+#define BS_T(k, f) do { } while (0)
 #endif
 
 constexpr int F3_HEAD = 192 + 64;    // doubles in front of the panel: 2 x 96 inverse diagonal blocks (also the stage-1
@@ -364,13 +367,11 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         }
     };
     // finished block column jb -> global factor (rows from its diagonal block down; nothing above is ever read)
-    auto store_block = [&](int jb, int t0, int nt) {
+    auto store_block = [&](int jb, int t0, int nt) {      // t0 / nt: first thread and number of threads taking part
         if (!P_SMEM) return;
-        const int c0 = 9 * jb, nr = Rf - c0;
-        for (int idx = t0; idx < 9 * nr; idx += nt) {
-            const int q = idx / nr, i = c0 + idx - q * nr;
-            Lg[i + (size_t)(c0 + q) * Rf] = P[i + (c0 + q) * ld];
-        }
+        const int c0 = 9 * jb, w0 = t0 >> 5, nw = nt >> 5;          // whole warps: one column at a time, lanes along the rows
+        for (int q = w0; q < 9; q += nw)
+            for (int i = c0 + lane; i < Rf; i += 32) Lg[i + (size_t)(c0 + q) * Rf] = P[i + (c0 + q) * ld];
     };
     // U -= L21[:, blocks] L21[:, blocks]^T over the lower triangle (+ rhs row).  Register tiles of 2 rows x 8 columns with
     // the lanes of a warp along the ROWS: the row operand is one 16-byte load per lane, contiguous across the warp, the
@@ -542,10 +543,15 @@ __host__ __device__ __forceinline__ long long bs3_smem_doubles(int Rf, int Cf, b
     return Rb + Cf + 16 + 9LL * Cf + (staged ? (long long)Rf * Cf : 0);
 }
 
+// `chained` (top of the tree, all fronts of several levels in ONE launch, parents first in the grid, everything
+// co-resident): a front waits for its parent through a per-front completion counter instead of a kernel boundary — the
+// front may start when its parent has completed one solve more than itself — so the levels with 1..64 fronts cost one
+// flag round trip each instead of a launch + drain each.  n_late: the first n_late CTAs (the top level) stage their factor
+// after the grid dependency (the kernel before may still be writing it); everything else prefetches before it.
 __global__ void __launch_bounds__(BS3_THREADS)
 k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3Meta m,
              const double* __restrict__ Lbuf, const double* __restrict__ Linv, double* __restrict__ D, int force,
-             int smem_doubles, int pre_ok) {
+             int smem_doubles, int n_late, int chained, int* __restrict__ count, int dense_root) {
     const int f = fronts[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NW = BS3_THREADS / 32;
@@ -560,18 +566,43 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     double* sLi = xs + 16;             // [nbs][81] inverse diagonal blocks
     double* sP = sLi + 81 * nbs;       // [Rf x Cf] panel copy (if it fits)
     const bool staged = (bs3_smem_doubles(Rf, Cf, true) <= smem_doubles);
-    // pre_ok: the previous kernel in the stream is the parent level of this very back-substitution, so the factor (L,
-    // Linv) was complete before it started: the panel is pulled into shared memory while the parents are still solving
+    const bool pre_ok = (int)blockIdx.x >= n_late;
+    BS_T(0, f); BS_T(3, f);
+    // the factor (L, Linv) of every front below the top level was complete before the previous kernel started: the panel
+    // is pulled into shared memory while the parents are still solving; the boundary variable ids are immutable
     auto stage_factor = [&]() {
         for (int i = tid; i < 81 * nbs; i += BS3_THREADS) sLi[i] = Linv[m.Ioff[f] + i];
         if (staged)
             for (int i = tid; i < Rf * Cf; i += BS3_THREADS) sP[i] = Lg[i];
     };
     if (pre_ok) stage_factor();
-    cudaGridDependencySynchronize();           // PDL: the parents' solution (and, for the root, the factor) is complete
+    int bvar[2] = {0, 0};              // this thread's boundary rows r = tid, tid + 512 -> index into D
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int r = tid + u * BS3_THREADS;
+        if (r < Rb) bvar[u] = 3 * vars[npad + r / 3] + (r % 3);
+    }
+    const int parent = chained ? m.parent[f] : -1;
+    cudaGridDependencySynchronize();           // PDL: the kernel before (parents' solution / the factor) is complete
     cudaTriggerProgrammaticLaunchCompletion();
     if (!force && !st->active) return;
-    for (int r = tid; r < Rb; r += BS3_THREADS) xb[r] = D[3 * (size_t)vars[npad + r / 3] + (r % 3)];
+    int mine = 0;
+    if (chained) {
+        if (tid == 0) {
+            mine = *(volatile int*)(count + f);
+            if (parent >= 0 && parent != dense_root)
+                while (*(volatile int*)(count + parent) != mine + 1) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    BS_T(1, f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int r = tid + u * BS3_THREADS;
+        if (r < Rb) xb[r] = D[bvar[u]];
+    }
+    for (int r = tid + 2 * BS3_THREADS; r < Rb; r += BS3_THREADS) xb[r] = D[3 * (size_t)vars[npad + r / 3] + (r % 3)];
     if (!pre_ok) stage_factor();
     const double* Lp = staged ? sP : Lg;
     __syncthreads();
@@ -605,6 +636,12 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
         __syncthreads();
     }
     for (int c = tid; c < 3 * np; c += BS3_THREADS) D[3 * (size_t)vars[c / 3] + (c % 3)] = ts[c];
+    if (chained) {                             // publish: the solution is written before the counter moves
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *(volatile int*)(count + f) = mine + 1;
+    }
+    BS_T(2, f);
 }
 
 }  // namespace islam

@@ -37,3 +37,18 @@ for l in range(plan['n_levels']):
           f'CTA resident before dep {np.median(dep - start) / 1e3:6.1f} us  max fronts per SM {cnt.max()}  SMs used {len(cnt)}')
     prev_end = end.max()
 print('total', (t[2][:plan["F"]].max() - t0) / 1e3, 'us')
+# back-substitution: CTA start / dependency (or parent counter) passed / end
+L.islam_debug_bs_times(buf)
+t = np.array(buf[:], dtype=np.uint64).reshape(4, 8192).astype(np.int64)
+prev_end = None
+print('back-substitution (root level first)')
+for l in range(plan['n_levels'] - 1, -1, -1):
+    fs = np.where(lv == l)[0]
+    fs = fs[fs < 8192]
+    start, dep, end = t[0][fs], t[1][fs], t[2][fs]
+    dur = (end - dep) / 1e3
+    gap = (dep.min() - prev_end) / 1e3 if prev_end is not None else 0.0
+    print(f'level {l:2d} fronts {len(fs):4d}  level wall {(end.max() - dep.min()) / 1e3:7.1f} us  gap after parents {gap:6.1f} us  '
+          f'front dur min/med/max {dur.min():6.1f}/{np.median(dur):6.1f}/{dur.max():6.1f} us  resident before go {np.median(dep - start) / 1e3:6.1f} us')
+    prev_end = end.max()
+print('total', (t[2][:plan['F']].max() - t[1][:plan['F']].min()) / 1e3, 'us')
