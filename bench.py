@@ -198,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
     ms = float(t.item())
     iters_total = LM_ITERS * args.steps                  # one graph, however many GPUs share it
     value = iters_total / (ms * 1e-3)
-    launches = tries * (7 + 2 * s.dims.levels)     # begin_try, factors, assemble, begin_step, L x factor, L x back-substitution, retract, trial factors, end_try
+    launches = tries * (7 + s.dims.levels + s.dims.bs_launches)   # begin_try, factors, assemble, begin_step, one factor launch per level, back-substitution (top levels chained in one launch), retract, trial factors, end_try
 
     # ---- per-phase device time of one try (CUDA events on the solver's stream) -> roofline of the dominant kernel
     one_step()

@@ -53,7 +53,7 @@ typedef struct islam_pvgo_dims {
     int32_t band, root_pivots;
     int32_t max_rows, max_cols;
     int32_t n_shared_fronts; /* fronts factored redundantly on every rank (multi-GPU) */
-    int32_t reserved;
+    int32_t bs_launches;     /* kernel launches of one back-substitution (top levels are chained inside one launch) */
     int64_t L_doubles, U_doubles;
     int64_t shared_doubles;  /* length of the per-try all-reduce buffer (multi-GPU) */
     double factor_flops;

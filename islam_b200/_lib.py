@@ -19,7 +19,7 @@ class PvgoOpts(C.Structure):
 class PvgoDims(C.Structure):
     _fields_ = [('N', C.c_int32), ('E', C.c_int32), ('M', C.c_int32), ('P', C.c_int32), ('F', C.c_int32),
                 ('levels', C.c_int32), ('band', C.c_int32), ('root_pivots', C.c_int32), ('max_rows', C.c_int32),
-                ('max_cols', C.c_int32), ('n_shared_fronts', C.c_int32), ('reserved', C.c_int32),
+                ('max_cols', C.c_int32), ('n_shared_fronts', C.c_int32), ('bs_launches', C.c_int32),
                 ('L_doubles', C.c_int64), ('U_doubles', C.c_int64), ('shared_doubles', C.c_int64),
                 ('factor_flops', C.c_double)]
 

@@ -497,6 +497,9 @@ extern "C" int islam_pvgo_get_dims(const islam_pvgo* h, islam_pvgo_dims* d) {
     d->root_pivots = q.root_pivots / 2; d->max_rows = q.max_rows; d->max_cols = q.max_cols;
     d->n_shared_fronts = h->n_shared; d->L_doubles = q.L_doubles; d->U_doubles = q.U_doubles;
     d->shared_doubles = h->shared_doubles; d->factor_flops = q.factor_flops;
+    d->bs_launches = (h->bs_chain_n > 0 ? 1 : 0);
+    for (int l = (h->bs_chain_n > 0 ? h->bs_chain_from : q.n_levels) - 1; l >= 0; --l)
+        d->bs_launches += (h->level_nlocal[l] + h->level_nshared[l]) > 0;
     return 0;
 }
 
