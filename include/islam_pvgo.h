@@ -11,6 +11,7 @@
  *   pvgo.py:114-119    align_to                                        -> islam_pvgo_align
  *   imu_integrator.py:69-164 + pp.module.IMUPreintegrator.forward      -> islam_imu_preintegrate
  *   PyPose LieTensor Exp/Log/Inv/Mul/Act (+ left-tangent backward)     -> islam_lie_* (elementwise)
+ *   dense_ba.py:88-176 scale_from_disp_flow (TartanVO.py:159-171)      -> islam_scale_from_disp_flow (batched)
  *
  * Conventions
  *   - All tensor arguments are raw DEVICE pointers to contiguous row-major float32 (or as stated) buffers
@@ -170,6 +171,17 @@ int islam_imu_preintegrate(const float* acc /* S x 3 */, const float* gyro /* S 
                            float gravity, int32_t motion_mode, float* pos, float* rot, float* vel,
                            void* workspace /* islam_imu_workspace_bytes(S,K) */, void* stream);
 int64_t islam_imu_workspace_bytes(int32_t S, int32_t K);
+
+/* ---- metric scale of the VO translation (dense_ba.py:88-176 scale_from_disp_flow; call site TartanVO.py:159-171) ---- */
+/* One fused pass over a batch of B samples (the reference loops over samples in Python).  disp B x H x W (or NULL when
+ * depth is given), flow B x 2 x H x W, motion B x 7 (SE3, frame k -> k+1 as TartanVO reports it), intr B x 4 (fx, fy, cx, cy),
+ * baseline B, depth B x H x W or NULL, mask_in B x H x W bytes or NULL (the Canny edge mask), disp_th B.
+ * Outputs: scale B, z B x H x W, mask / depth_mask B x H x W bytes, mask_count B (nullable; the reference warns below 500). */
+int islam_scale_from_disp_flow(const float* disp, const float* flow, const float* motion, const float* intr,
+                               const float* baseline, const float* depth, const uint8_t* mask_in, const float* disp_th,
+                               int32_t B, int32_t H, int32_t W, float* scale, float* z, uint8_t* mask, uint8_t* depth_mask,
+                               int32_t* mask_count, void* workspace /* islam_scale_workspace_bytes(B,H,W) */, void* stream);
+int64_t islam_scale_workspace_bytes(int32_t B, int32_t H, int32_t W);
 
 /* ---- elementwise LieTensor maps (forward + left-tangent backward), n elements ------------------------- */
 enum { ISLAM_SE3 = 0, ISLAM_SO3 = 1 };

@@ -79,6 +79,8 @@ _SIGS = {
     'islam_imu_preintegrate': (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_float, C.c_int32, _P, _P, _P,
                                          _P, _P]),
     'islam_imu_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
+    'islam_scale_from_disp_flow': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'islam_scale_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     'islam_lie_exp': (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     'islam_lie_log': (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     'islam_lie_inv': (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib', 'libislam_pvgo.so')
-SOURCES = ['pvgo.cu', 'imu.cu', 'lieops.cu', 'symbolic.cpp', 'symbolic3.cpp']
+SOURCES = ['pvgo.cu', 'imu.cu', 'lieops.cu', 'scale.cu', 'symbolic.cpp', 'symbolic3.cpp']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
 

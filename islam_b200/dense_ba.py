@@ -1,0 +1,75 @@
+"""Mirror of the one function of /root/reference/dense_ba.py that sits immediately before the PVGO back-end:
+`scale_from_disp_flow` (dense_ba.py:88-176, called per sample at TartanVO.py:159-171).
+
+Same arguments, same four return values.  `scale_from_disp_flow_batch` does the whole batch of TartanVO.py's Python loop
+in one fused kernel launch.  There is no CPU path."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import IslamError
+from .pvgo import _plain
+
+
+def _f(t, dev, shape=None):
+    t = _plain(t).detach().to(device=dev, dtype=torch.float32).contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise IslamError(f'expected shape {tuple(shape)}, got {tuple(t.shape)}')
+    return t
+
+
+def scale_from_disp_flow_batch(disp, flow, motion, intrinsics, baseline, depth=None, mask=None, disp_th=1.0, device=None):
+    """disp (B,H,W) [ignored when depth is given], flow (B,2,H,W), motion (B,7) SE3, intrinsics (B,4) = fx,fy,cx,cy,
+    baseline (B,), depth (B,H,W) | None, mask (B,H,W) bool | None, disp_th float | (B,).
+    Returns scale (B,), z (B,H,W), mask (B,H,W) bool, depth_mask (B,H,W) bool, mask_count (B,) int32 — on the device."""
+    flow_t = _plain(flow)
+    dev = torch.device(device) if device is not None else (flow_t.device if flow_t.is_cuda else torch.device('cuda', torch.cuda.current_device()))
+    if dev.type != 'cuda':
+        raise IslamError('scale_from_disp_flow needs a CUDA device: there is no CPU fallback')
+    flow_t = _f(flow_t, dev)
+    B, two, H, W = flow_t.shape
+    if two != 2:
+        raise IslamError('flow must be (B, 2, H, W)')
+    mo = _f(motion, dev)
+    if mo.shape[-1] == 6:                       # dense_ba.py:92-95: an se3 input goes through Exp first
+        from .pypose_compat import _ops
+        mo = _ops.ExpFn.apply(mo, _ops.SE3)
+    elif mo.shape[-1] != 7:
+        raise IslamError('motion must be SE3 (7 numbers) or se3 (6 numbers)')
+    mo = mo.reshape(B, 7).contiguous()
+    intr = _f(intrinsics, dev, (B, 4))
+    bl = _f(torch.as_tensor(baseline).reshape(-1), dev, (B,))
+    th = torch.as_tensor(disp_th, dtype=torch.float32).reshape(-1)
+    th = _f(th.expand(B) if th.numel() == 1 else th, dev, (B,))
+    d = _f(disp, dev, (B, H, W)) if depth is None else None
+    dep = _f(depth, dev, (B, H, W)) if depth is not None else None
+    m_in = _plain(mask).to(device=dev, dtype=torch.uint8).contiguous() if mask is not None else None
+    if m_in is not None and tuple(m_in.shape) != (B, H, W):
+        raise IslamError(f'expected mask shape {(B, H, W)}, got {tuple(m_in.shape)}')
+    L = _lib.lib()
+    ws = torch.empty(int(L.islam_scale_workspace_bytes(B, H, W)), dtype=torch.uint8, device=dev)
+    scale = torch.empty(B, dtype=torch.float32, device=dev)
+    z = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+    m_out = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    dm_out = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.islam_scale_from_disp_flow(p(d), p(flow_t), p(mo), p(intr), p(bl), p(dep), p(m_in), p(th), B, H, W, p(scale), p(z),
+                                                p(m_out), p(dm_out), p(cnt), p(ws), st), 'islam_scale_from_disp_flow')
+    return scale, z, m_out.bool(), dm_out.bool(), cnt
+
+
+def scale_from_disp_flow(disp, flow, motion, fx, fy, cx, cy, baseline, depth=None, mask=None, disp_th=1):
+    """dense_ba.py:88 — one sample: disp (H,W), flow (2,H,W), motion SE3 (7,).  Returns (s (1,), z (H,W), mask, depth_mask)."""
+    mo = _plain(motion)
+    dev = mo.device if mo.is_cuda else None
+    intr = torch.tensor([[float(fx), float(fy), float(cx), float(cy)]], dtype=torch.float32)
+    un = lambda t: None if t is None else _plain(t).unsqueeze(0)
+    s, z, m, dm, cnt = scale_from_disp_flow_batch(un(disp), un(flow), mo.reshape(1, -1), intr, torch.tensor([float(baseline)]),
+                                                 depth=un(depth), mask=un(mask), disp_th=float(disp_th), device=dev)
+    if int(cnt.item()) < 500:
+        print('Warning! mask contains too less points!', int(cnt.item()))          # dense_ba.py:134-135
+    return s.view(1), z[0], m[0], dm[0]
