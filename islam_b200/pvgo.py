@@ -157,7 +157,10 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
     transvel_infos = np.ones(n_nodes - 1) * loss_weight[3] ** 2
 
     graph = PoseVelGraph(init_nodes, init_vels, reproj, links=links, device=device)
-    graph._ensure(links, _plain(vo_motions).detach(), imu_drots, imu_dtrans, imu_dvels, dts, loss_weight)
+    # one host -> device transfer of the VO motions serves both the optimisation (detached, pvgo.py:146) and the outer
+    # loss (autograd-connected, pvgo.py:186-187); .to() is differentiable, so the gradient still reaches the caller's tensor
+    vo_dev = _plain(vo_motions).to(device=graph._device, dtype=torch.float32, non_blocking=True)
+    graph._ensure(links, vo_dev.detach(), imu_drots, imu_dtrans, imu_dvels, dts, loss_weight)
     s = graph.solver
     # pvgo.py:169-180: LM(min=1e-4) + Cholesky + TrustRegion(radius) + StopOnPlateau(steps=10, patience=3, 1e-3)
     s.lm_reset(radius=float(radius), lm_min=1e-4, max_steps=int(max_steps), patience=int(patience),
@@ -167,15 +170,21 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
         print('Linear solver failed. Breaking optimization step...')            # PyPose's message (A.4)
 
     if target == 'vo':                                                          # pvgo.py:186-189
-        trans_loss, rot_loss = graph.vo_loss(links, vo_motions)
+        trans_loss, rot_loss = graph.vo_loss(links, vo_dev)
     elif target == 'imu':
         trans_loss, rot_loss = graph.imu_loss(imu_drots, imu_dvels)
     else:
         raise ValueError(f'unknown target {target!r}')
 
     nodes, vels = graph.align_to(_plain(init_nodes)[0])                         # pvgo.py:195
-    nodes = _wrap_like(init_nodes, _plain(nodes).detach().cpu(), 'SE3_type')
-    vels = vels.detach().cpu()
+    # nodes.cpu(), vels.cpu() (pvgo.py:196-197) as two asynchronous copies into pinned memory and ONE synchronisation
+    nodes_h = torch.empty(nodes.shape, dtype=nodes.dtype, pin_memory=True)
+    vels_h = torch.empty(vels.shape, dtype=vels.dtype, pin_memory=True)
+    nodes_h.copy_(_plain(nodes).detach(), non_blocking=True)
+    vels_h.copy_(vels.detach(), non_blocking=True)
+    torch.cuda.current_stream(graph._device).synchronize()
+    nodes = _wrap_like(init_nodes, nodes_h, 'SE3_type')
+    vels = vels_h
     covs = {'vo_rot': vo_rot_infos, 'imu_rot': imu_rot_infos, 'vo_trans': vo_trans_infos,
             'imu_vel': imu_vel_infos, 'transvel': transvel_infos}               # pvgo.py:199-203
     run_pvgo.last_state = st

@@ -17,7 +17,8 @@ def _ptr(t):
 def _f32(t, device, shape=None):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
-    t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+    # non_blocking: a pinned host source is copied asynchronously on the current stream (the solver's stream waits for it)
+    t = t.detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise IslamError(f'expected shape {tuple(shape)}, got {tuple(t.shape)}')
     return t
