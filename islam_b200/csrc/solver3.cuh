@@ -474,6 +474,51 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         } else {
             // trailing update: column block cb only needs rows >= 9 cb (lower trapezoid); the 9 diagonal rows of block
             // jb+1 are warp 0's
+            if (P_SMEM) {
+                // register tiles of 2 rows x the 9 columns of one block, lanes along the rows: the row operand is one
+                // aligned 16-byte load per lane (pairs start at the parity of Cf, see the panel shift above), the nine
+                // column operands are broadcast loads, and the read-modify-write is one 16-byte access per column
+                const int par = Cf & 1;
+                auto first_pair = [&](int cb) { const int rmin = 9 * cb + (cb == jb + 1 ? 9 : 0); return (rmin - par) >> 1; };
+                const int last_pair = (Rf - 1 - par) >> 1;
+                int tasks = 0;
+                for (int cb = jb + 1; cb < nbs; ++cb) tasks += last_pair - first_pair(cb) + 1;
+                for (int t = tid - 32; t < tasks; t += NT - 32) {
+                    int cb = jb + 1, rem = t;
+                    while (rem >= last_pair - first_pair(cb) + 1) { rem -= last_pair - first_pair(cb) + 1; ++cb; }
+                    const int i0 = par + 2 * (first_pair(cb) + rem), j0 = 9 * cb;
+                    const int rmin = j0 + (cb == jb + 1 ? 9 : 0);
+                    const bool v0 = i0 >= rmin, v1 = i0 + 1 < Rf;         // (i0 + 1 >= rmin and i0 < Rf always hold)
+                    double acc[2][9];
+#pragma unroll
+                    for (int y = 0; y < 9; ++y) { acc[0][y] = 0.0; acc[1][y] = 0.0; }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const double* col = P + (c0 + q) * ld;
+                        const double2 a = *reinterpret_cast<const double2*>(col + i0);
+#pragma unroll
+                        for (int y = 0; y < 9; ++y) {
+                            const double bv = col[j0 + y];
+                            acc[0][y] += a.x * bv; acc[1][y] += a.y * bv;
+                        }
+                    }
+                    if (v0 && v1) {
+#pragma unroll
+                        for (int y = 0; y < 9; ++y) {
+                            double2* dst = reinterpret_cast<double2*>(P + i0 + (j0 + y) * ld);
+                            double2 u = *dst;
+                            u.x -= acc[0][y]; u.y -= acc[1][y];
+                            *dst = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int y = 0; y < 9; ++y) {
+                            if (v0) P[i0 + (j0 + y) * ld] -= acc[0][y];
+                            if (v1) P[i0 + 1 + (j0 + y) * ld] -= acc[1][y];
+                        }
+                    }
+                }
+            } else {
             int tasks = 0;
             for (int cb = jb + 1; cb < nbs; ++cb) tasks += 3 * ((Rf - 9 * cb + 3) >> 2);
             for (int t = tid - 32; t < tasks; t += NT - 32) {
@@ -513,6 +558,7 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
                     if (vx[x])
 #pragma unroll
                         for (int y = 0; y < 3; ++y) P[ix[x] + (jc + y) * ld] -= acc[x][y];
+            }
             }
             store_block(jb, tid - 32, NT - 32);
             if (schur_now) schur_blocks(pend_first, schur_to, tid - 32, NT - 32);
