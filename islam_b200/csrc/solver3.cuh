@@ -388,55 +388,67 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     };
     int tp_first = 0, tc_first = 0;            // the first tile of this thread in the shadowed steps (threads 32..NT-1)
     if (tid >= 32 && tid - 32 < ntiles) tile_of(tid - 32, tp_first, tc_first);
-    auto schur_blocks = [&](int jb0, int jb1, int t0, int nt) {     // block columns [jb0, jb1)
-        const int c0 = 9 * jb0, kn = 9 * (jb1 - jb0);
-        if (kn <= 0) return;
-        for (int t = t0; t < ntiles; t += nt) {
-            int tp, tc;
-            if (t == tid - 32) { tp = tp_first; tc = tc_first; }
-            else tile_of(t, tp, tc);
-            const int r0 = 2 * tp, s0 = 8 * tc;
-            double acc[2][8];
-#pragma unroll
-            for (int y = 0; y < 8; ++y) { acc[0][y] = 0.0; acc[1][y] = 0.0; }
-            const double* pa = P + Cf + r0 + c0 * ld;
-            const double* pb = P + Cf + s0 + c0 * ld;
-            if (P_SMEM) {
+    // rank-(kn) contribution of panel columns [c0, c0 + kn) to the 2 x 8 tile (tp, tc), accumulated in registers
+    auto schur_tile = [&](int tp, int tc, int c0, int kn, double (&acc)[2][8]) {
+        const int r0 = 2 * tp, s0 = 8 * tc;
+        const double* pa = P + Cf + r0 + c0 * ld;
+        const double* pb = P + Cf + s0 + c0 * ld;
+        if (P_SMEM) {
 #pragma unroll 3
-                for (int k = 0; k < kn; ++k) {
-                    const double2 a = *reinterpret_cast<const double2*>(pa + k * ld);
-                    double2 b[4];
+            for (int k = 0; k < kn; ++k) {
+                const double2 a = *reinterpret_cast<const double2*>(pa + k * ld);
+                double2 b[4];
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) b[y] = *reinterpret_cast<const double2*>(pb + k * ld + 2 * y);
+                for (int y = 0; y < 4; ++y) b[y] = *reinterpret_cast<const double2*>(pb + k * ld + 2 * y);
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        acc[0][2 * y] += a.x * b[y].x; acc[0][2 * y + 1] += a.x * b[y].y;
-                        acc[1][2 * y] += a.y * b[y].x; acc[1][2 * y + 1] += a.y * b[y].y;
-                    }
-                }
-            } else {
-                // panel in global memory: scalar operand loads (rows past the panel read as zero)
-#pragma unroll 3
-                for (int k = 0; k < kn; ++k) {
-                    const double a0 = pa[k * ld], a1 = (Cf + r0 + 1 < Rf) ? pa[k * ld + 1] : 0.0;
-#pragma unroll
-                    for (int y = 0; y < 8; ++y) {
-                        const double b = (Cf + s0 + y < Rf) ? pb[k * ld + y] : 0.0;
-                        acc[0][y] += a0 * b; acc[1][y] += a1 * b;
-                    }
+                for (int y = 0; y < 4; ++y) {
+                    acc[0][2 * y] += a.x * b[y].x; acc[0][2 * y + 1] += a.x * b[y].y;
+                    acc[1][2 * y] += a.y * b[y].x; acc[1][2 * y + 1] += a.y * b[y].y;
                 }
             }
+        } else {
+            // panel in global memory: scalar operand loads (rows past the panel read as zero)
+#pragma unroll 3
+            for (int k = 0; k < kn; ++k) {
+                const double a0 = pa[k * ld], a1 = (Cf + r0 + 1 < Rf) ? pa[k * ld + 1] : 0.0;
 #pragma unroll
-            for (int y = 0; y < 8; ++y) {
-                const int s_ = s0 + y;
-                if (s_ >= ub || r0 + 1 < s_) continue;                 // the pair (r0, r0+1) lies above column s_
-                double2* up = reinterpret_cast<double2*>(Uw + f3_ucol(s_, ub) + r0);
-                if (u_direct) *up = make_double2(-acc[0][y], -acc[1][y]);
-                else { double2 u = *up; u.x -= acc[0][y]; u.y -= acc[1][y]; *up = u; }
+                for (int y = 0; y < 8; ++y) {
+                    const double b = (Cf + s0 + y < Rf) ? pb[k * ld + y] : 0.0;
+                    acc[0][y] += a0 * b; acc[1][y] += a1 * b;
+                }
             }
         }
     };
-    int pend_first = 0;                        // first finished block column not yet applied to U
+    // U[tile] -= acc  (or = -acc for a leaf that writes its update matrix once)
+    auto schur_apply = [&](int tp, int tc, const double (&acc)[2][8]) {
+        const int r0 = 2 * tp, s0 = 8 * tc;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int s_ = s0 + y;
+            if (s_ >= ub || r0 + 1 < s_) continue;                     // the pair (r0, r0+1) lies above column s_
+            double2* up = reinterpret_cast<double2*>(Uw + f3_ucol(s_, ub) + r0);
+            if (u_direct) *up = make_double2(-acc[0][y], -acc[1][y]);
+            else { double2 u = *up; u.x -= acc[0][y]; u.y -= acc[1][y]; *up = u; }
+        }
+    };
+    // Every thread of warps 1.. owns ONE tile whose accumulators stay in registers through all steps (a rank-9
+    // contribution per step, in the shadow of the diagonal chain) and touch U once, at the end.  Tiles beyond that (wide
+    // boundaries, or the 256- / 128-thread variants) are done in one pass over all pivot columns after the last step.
+    const bool has_tile = tid >= 32 && tid - 32 < ntiles;
+    double sacc[2][8];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) { sacc[0][y] = 0.0; sacc[1][y] = 0.0; }
+    auto schur_rest = [&]() {
+        for (int t = tid - 32 + (NT - 32); t < ntiles; t += NT - 32) {
+            int tp, tc;
+            tile_of(t, tp, tc);
+            double acc[2][8];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) { acc[0][y] = 0.0; acc[1][y] = 0.0; }
+            schur_tile(tp, tc, 0, Cf, acc);
+            schur_apply(tp, tc, acc);
+        }
+    };
     if (warp == 0) diag_block(0, false, sLinv);
     __syncthreads();
     for (int jb = 0; jb < nbs; ++jb) {
@@ -462,13 +474,12 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
         __syncthreads();
         PHASE(11 + 3 * jb);
         const int ncb = nbs - 1 - jb;
-        // finished block columns enter U two at a time (rank 18: half the read-modify-write passes over U), in the even
-        // steps from the third on, where the trailing update has become light; the rest in the last step
-        const bool schur_now = ncb == 0 || (!u_direct && jb >= 2 && (jb & 1) == 0);
-        const int schur_to = ncb == 0 ? nbs : jb;
         if (ncb == 0) {                        // last block column: nothing left on the serial chain
             store_block(jb, tid, NT);
-            schur_blocks(pend_first, schur_to, tid, NT);
+            if (tid >= 32) {
+                if (has_tile) { schur_tile(tp_first, tc_first, c0, 9, sacc); schur_apply(tp_first, tc_first, sacc); }
+                schur_rest();
+            }
         } else if (warp == 0) {                // the serial chain: next diagonal block (update + Cholesky + inverse)
             diag_block(jb + 1, true, sLinv + 96 * ((jb + 1) & 1));
         } else {
@@ -561,9 +572,8 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             }
             }
             store_block(jb, tid - 32, NT - 32);
-            if (schur_now) schur_blocks(pend_first, schur_to, tid - 32, NT - 32);
+            if (has_tile) schur_tile(tp_first, tc_first, c0, 9, sacc);
         }
-        if (schur_now) pend_first = schur_to;
         __syncthreads();
         PHASE(12 + 3 * jb);
     }
