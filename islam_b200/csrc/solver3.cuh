@@ -646,8 +646,11 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     if (chained) {
         if (tid == 0) {
             mine = *(volatile int*)(count + f);
-            if (parent >= 0 && parent != dense_root)
-                while (*(volatile int*)(count + parent) != mine + 1) { }
+            if (parent >= 0 && parent != dense_root) {
+                const long long t0 = clock64();            // the parent is co-resident and earlier in the grid; the bound
+                while (*(volatile int*)(count + parent) != mine + 1)          // only guards against a wedged device
+                    if (clock64() - t0 > (1LL << 31)) break;
+            }
             __threadfence();
         }
         __syncthreads();
