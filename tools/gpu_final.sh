@@ -11,4 +11,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fa
 timeout 200 python tools/level_timeline.py > gpurun_out/timeline.log 2>&1
 timeout 200 python tools/phase_clocks.py 1 4 64 256 512 > gpurun_out/phase.log 2>&1
 timeout 200 python tools/scale_bench.py > gpurun_out/scale_bench.log 2>&1
+timeout 600 python tools/configs_bench.py > gpurun_out/configs.log 2>&1
 tail -3 gpurun_out/t_gpu_all.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench_n1.json | cut -c1-300; cat gpurun_out/bench_ref.json | cut -c1-300; tail -12 gpurun_out/timeline.log

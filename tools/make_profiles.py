@@ -157,4 +157,5 @@ if __name__ == '__main__':
     copy_text('timeline.log', f'{TAG}_level_timeline.txt', '# tools/level_timeline.py: globaltimer per front of one C2 factorisation (libislam_dbg.so)\n')
     copy_text('phase.log', f'{TAG}_factor_phase_clocks.txt', '# tools/phase_clocks.py: clock64() stamps of the middle CTA of a level, per grid size (libislam_dbg.so)\n')
     copy_text('scale_bench.log', f'{TAG}_scale_microbench.txt', '# tools/scale_bench.py: islam_scale_from_disp_flow (SURVEY 8f rank 4)\n')
+    copy_text('configs.log', f'{TAG}_configs.txt', '# tools/configs_bench.py: every BASELINE.json config on one B200\n')
     print(sorted(os.listdir(PROF)))
