@@ -956,7 +956,10 @@ extern "C" int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out, void* strea
     if (!h) return -1;
     if (h->opts.n_parts > 1) return -6;
     cudaStream_t s = (cudaStream_t)stream;
-    int budget = h->prm.max_steps + 2;          // speculative: a couple of rejected tries cost no extra sync
+    // speculative: surplus tries are predicated off on the device, but each still costs ~20 (empty) kernel launches.
+    // Fixed step count: exactly max_steps accepted tries are coming, + 2 for rejected ones.  With the plateau scheduler the
+    // loop usually stops after a few steps (9-pose windows of train.py: 2-4), so go in rounds of 4.
+    int budget = h->prm.use_scheduler ? std::min(h->prm.max_steps + 2, 4) : h->prm.max_steps + 2;
     for (int guard = 0; guard < 64; ++guard) {
         for (int k = 0; k < budget; ++k) {
             int rc = graph_try(h, s);

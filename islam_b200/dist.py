@@ -101,7 +101,8 @@ class ShardedPVGO:
         surplus tries no-ops); one synchronisation at the end, more only if rejected tries exhaust the budget."""
         s = self.s
         s._enter()
-        budget = (s.params.max_steps + 2) if budget is None else budget
+        if budget is None:                      # same policy as islam_pvgo_lm_run
+            budget = min(s.params.max_steps + 2, 4) if s.params.use_scheduler else s.params.max_steps + 2
         for _ in range(64):
             for _ in range(budget):
                 self.lm_try()
