@@ -19,8 +19,8 @@
  *   - Every call takes the cudaStream_t to enqueue on (as void*), is asynchronous unless stated, and is
  *     CUDA-graph capturable except the functions marked "synchronises".
  *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.  islam_pvgo_create: -2 bad edge list,
- *     -5 boundary too wide for the back-substitution kernel, -7 loop-closure root above 256 poses (dense-root path
- *     not implemented yet).
+ *     -5 boundary too wide for the back-substitution kernel, -6 dense loop-closure root with n_parts > 1 (the dense
+ *     root is single-GPU), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
  *   - Numerical failure of the Cholesky (non-positive pivot / NaN) does not abort: it raises `info` in the
  *     LM state, and the step is abandoned exactly as PyPose's "Linear solver failed. Breaking..." path.
  *   - A handle is not thread-safe; use one per host thread / stream.
@@ -40,8 +40,8 @@ typedef struct islam_pvgo islam_pvgo;
 
 typedef struct islam_pvgo_opts {
     int32_t band_max;    /* edges with |i-j| above this are loop closures (root separator); default 16 */
-    int32_t leaf_max;    /* poses per leaf front; default 8 */
-    int32_t pivot_max;   /* poses eliminated per front; default 8 */
+    int32_t leaf_max;    /* a leaf front holds up to 3*leaf_max 3-dof variables (tau, phi, v of a pose); default 8 */
+    int32_t pivot_max;   /* a front eliminates up to 3*pivot_max variables = 9*pivot_max columns; default 8, max 21 */
     int32_t n_parts;     /* contiguous pose windows (multi-GPU sharding); default 1 */
     int32_t part;        /* this rank's window in [0, n_parts); default 0 */
     int32_t reserved[3];
@@ -51,7 +51,7 @@ typedef struct islam_pvgo_dims {
     int32_t N, E, M;         /* poses, VO/loop-closure edges, IMU pairs (N-1) */
     int32_t P;               /* unique off-diagonal 9x9 blocks of J^T W J */
     int32_t F, levels;       /* fronts, elimination-tree height */
-    int32_t band, root_pivots;
+    int32_t band, root_pivots;   /* longest short edge; loop-closure poses promoted to the root */
     int32_t max_rows, max_cols;
     int32_t n_shared_fronts; /* fronts factored redundantly on every rank (multi-GPU) */
     int32_t bs_launches;     /* kernel launches of one back-substitution (top levels are chained inside one launch) */
