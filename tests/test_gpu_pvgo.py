@@ -74,6 +74,29 @@ def test_solve_matches_dense(name):
     assert err < 1e-7, (name, err)
 
 
+@pytest.mark.parametrize('opts', [dict(leaf_max=3, pivot_max=2), dict(leaf_max=16, pivot_max=4), dict(band_max=4),
+                                  dict(leaf_max=1, pivot_max=1)])
+@pytest.mark.parametrize('name', ['band8_300', 'lc_400', 'band3_57'])
+def test_solve_matches_dense_with_other_front_shapes(name, opts):
+    """The same check on plans with other front shapes: narrow / chained pivot sets, wide leaves, a band threshold that turns
+    most of the band-8 edges into loop closures (a big ordinary root front with many children, update matrices in global
+    memory), single-variable-triplet fronts."""
+    g = GRAPHS[name]()
+    s = _solver(g, **opts)
+    s.linearize()
+    Hd, Ho, gg, pairs = [t.cpu().numpy() for t in s.normal_equations()]
+    H = _dense_from_blocks(g.N, Hd, Ho, pairs)
+    scale = 1.0 + 1e-4
+    D, info = s.solve(scale)
+    assert info == 0
+    d = np.clip(np.diag(H), 1e-4, 1e32) * scale
+    A = H.copy()
+    A[np.arange(len(d)), np.arange(len(d))] = d
+    Dref = np.linalg.solve(A, -gg.reshape(-1)).reshape(-1, 9)
+    err = np.abs(D.cpu().numpy() - Dref).max() / np.abs(Dref).max()
+    assert err < 1e-7, (name, opts, err)
+
+
 @pytest.mark.parametrize('name', ['C1', 'band8_300', 'lc_400'])
 def test_lm_steps_match_oracle(name):
     """optimizer.step by optimizer.step: loss, damping, reject counts and the final (aligned) poses."""
