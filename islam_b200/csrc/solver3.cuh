@@ -419,16 +419,18 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
             }
         }
     };
-    // U[tile] -= acc  (or = -acc for a leaf that writes its update matrix once)
+    // U_global[tile] = U[tile] - acc  (U: children's pass-through, in shared or global memory; none for a direct leaf)
     auto schur_apply = [&](int tp, int tc, const double (&acc)[2][8]) {
         const int r0 = 2 * tp, s0 = 8 * tc;
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
             const int s_ = s0 + y;
             if (s_ >= ub || r0 + 1 < s_) continue;                     // the pair (r0, r0+1) lies above column s_
-            double2* up = reinterpret_cast<double2*>(Uw + f3_ucol(s_, ub) + r0);
-            if (u_direct) *up = make_double2(-acc[0][y], -acc[1][y]);
-            else { double2 u = *up; u.x -= acc[0][y]; u.y -= acc[1][y]; *up = u; }
+            // the finished tile goes straight to the global update matrix (no separate copy of U out of shared memory)
+            const int off = f3_ucol(s_, ub) + r0;
+            double2 u = u_direct ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(Uw + off);
+            u.x -= acc[0][y]; u.y -= acc[1][y];
+            *reinterpret_cast<double2*>(Ug + off) = u;
         }
     };
     // Every thread of warps 1.. owns ONE tile whose accumulators stay in registers through all steps (a rank-9
@@ -579,8 +581,6 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
     }
     if (!ok && tid == 0) *chol_fail = 1;
     PHASE(4);
-    if (U_SMEM)
-        for (int i = tid; i < ulen; i += NT) Ug[i] = Uw[i];
 #ifdef ISLAM_PHASE_CLOCKS
     __syncthreads();
 #endif
