@@ -9,10 +9,13 @@
 // pivots pad the last block) and sees `nb` boundary variables.  Its frontal matrix lives in shared memory as
 //   P : (Cf + 3 nb + 1) x Cf column-major panel [F11; F21; rhs^T]   (the right-hand side b = -J^T W r rides along as
 //       one extra row, so the forward substitution is part of the factorisation)
-//   U : packed lower triangle of the (3 nb + 1)^2 boundary block (update matrix handed to the parent).
+//   U : lower triangle of the (3 nb + 1)^2 boundary block (update matrix handed to the parent), packed in column pairs
+//       that start at even offsets (f3_ucol below).
 // Assembly is "push": the panel is zeroed, the original 3x3 blocks of J^T W J are stored from a per-front list,
-// and each child's update matrix is streamed in (coalesced) and added through its boundary -> slot map, one
+// and the children's update matrices are streamed in (coalesced) and added at host-computed destinations, one
 // child after the other: a fixed summation order, no atomics, bitwise deterministic.
+// Factorisation: 9-column steps; warp 0 runs the serial chain of 9x9 diagonal blocks, warps 1.. do everything else in
+// its shadow (row solve, trailing update, store of finished columns, Schur update with register-resident tiles).
 #pragma once
 #include "common.cuh"
 
