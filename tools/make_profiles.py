@@ -126,7 +126,7 @@ def ncu_full():
     marks = [('preamble (zero fill, map resolution, pre-dependency A1)', 1), ('grid dependency + late A1 / stage 2', find('cudaGridDependencySynchronize();           // previous level')),
              ('A2 extend-add of the children', find('// A2. extend-add')), ('stage-1 dump', find('if (stage == 1) {                          // dump')),
              ('diagonal-block chain (warp 0)', find('auto diag_block = [&]')), ('store of finished block columns', find('auto store_block = [&]')),
-             ('Schur update U -= L21 L21^T', find('// U -= L21[:, blocks]')), ('step loop: Linv store, row solve, barriers', find('int pend_first = 0;')),
+             ('Schur update U -= L21 L21^T', find('// U -= L21[:, blocks]')), ('step loop: Linv store, row solve, barriers', find('if (warp == 0) diag_block(0, false, sLinv);')),
              ('trailing panel update', find('// trailing update: column block cb only')), ('tail (U store)', find('if (!ok && tid == 0) *chol_fail = 1;'))]
     marks = [m for m in marks if m[1]]
     agg, bar, inst = collections.Counter(), collections.Counter(), collections.Counter()
