@@ -279,8 +279,9 @@ def run_ours(args, rank, world, local_rank):
                    'parallelism': 'single GPU' if world == 1 else
                    f'{world} contiguous pose windows of ONE C2 graph; per LM try one NCCL all-reduce of the shared separator panels '
                    f'({s.dims.n_shared_fronts} fronts, {s.dims.shared_doubles * 8 / 1e6:.2f} MB); the trial sums travel through NVLink peer mailboxes inside the kernel that closes the try',
-                   'l2': f'working set (L {s.dims.L_doubles * 8 / 1e6:.0f} MB + U {s.dims.U_doubles * 8 / 1e6:.0f} MB '
-                         'fp64 panels) exceeds the 126 MB L2; no explicit flush'},
+                   'l2': (lambda d: f'no explicit flush: one LM iteration streams {(d.L_doubles * 8 + d.U_doubles * 10 + 648 * (d.N + d.P) + 336 * d.E) / 1e6:.0f} MB '
+                                    f'(L {d.L_doubles * 8 / 1e6:.0f} MB + U {d.U_doubles * 8 / 1e6:.0f} MB + destination maps {d.U_doubles * 2 / 1e6:.0f} MB + '
+                                    f'J^T W J blocks {648 * (d.N + d.P) / 1e6:.0f} MB + per-factor products {336 * d.E / 1e6:.0f} MB), more than the 126 MB L2')(s.dims)},
         'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
         'lm': {'final_loss': st.loss, 'steps_done': st.steps_done, 'tries': st.tries_total, 'info': st.info},
     }
