@@ -377,7 +377,8 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     if (max_optin <= 0) max_optin = 227 * 1024;
     set_factor_smem<512, 1, 2>(max_optin); set_factor_smem<512, 1, 1>(max_optin); set_factor_smem<512, 1, 0>(max_optin);
     set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin); set_factor_smem<128, 4, 1>(max_optin);
-    cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    const int bs_optin = max_optin - 64;       // the back-substitution kernel also has a few bytes of static shared memory (its mbarrier)
+    cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_optin);
     h->level_variant.assign(q.n_levels, 0);
     h->level_count.assign(q.n_levels, 0);
     h->n_sm = n_sm;
@@ -397,7 +398,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             if (opts.n_parts == 1 || q.f_part[f] < 0 || q.f_part[f] == opts.part) count[l]++;
         }
         for (int l = 0; l < q.n_levels; ++l) {
-            if (bs_min[l] > max_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
+            if (bs_min[l] > bs_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
             int var = need[2][l] <= max_optin ? 2 : (need[1][l] <= max_optin ? 1 : 0);
             long long bytes = need[var][l];
             // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency);
@@ -407,7 +408,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             h->level_variant[l] = var;
             h->level_count[l] = count[l];
             h->level_smem_bytes[l] = (int)bytes;
-            h->level_bs_bytes[l] = (int)(bs_full[l] <= max_optin ? bs_full[l] : bs_min[l]);
+            h->level_bs_bytes[l] = (int)(bs_full[l] <= bs_optin ? bs_full[l] : bs_min[l]);
         }
         for (int l = h->bs_chain_from; l < q.n_levels; ++l) h->bs_chain_bytes = std::max(h->bs_chain_bytes, h->level_bs_bytes[l]);
     }

@@ -599,7 +599,30 @@ k_factor3(const LMState* __restrict__ st, const int* __restrict__ fronts, Front3
 constexpr int BS3_THREADS = 512;
 __host__ __device__ __forceinline__ long long bs3_smem_doubles(int Rf, int Cf, bool staged) {
     const int Rb = Rf - Cf - 1;
-    return Rb + Cf + 16 + 9LL * Cf + (staged ? (long long)Rf * Cf : 0);
+    return ((Rb + Cf + 16 + 9LL * Cf + 1) & ~1LL) + (staged ? (long long)Rf * Cf + 2 : 0);      // panel copy 16-byte aligned
+}
+
+// ---- TMA (bulk asynchronous copy engine), 1-D form: global -> shared, completion on an mbarrier -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// true when the phase with the given parity has completed; gives up after ~1 s (the caller then copies by hand)
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+    const long long t0 = clock64();
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > (1LL << 31)) return false;
+    }
+    return true;
 }
 
 // `chained` (top of the tree, all fronts of several levels in ONE launch, parents first in the grid, everything
@@ -623,16 +646,21 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     double* ts = xb + Rb;              // [Cf]
     double* xs = ts + Cf;              // [16]
     double* sLi = xs + 16;             // [nbs][81] inverse diagonal blocks
-    double* sP = sLi + 81 * nbs;       // [Rf x Cf] panel copy (if it fits)
+    double* sP = smem + ((Rb + Cf + 16 + 81 * nbs + 1) & ~1);      // [Rf x Cf] panel copy (if it fits), 16-byte aligned
     const bool staged = (bs3_smem_doubles(Rf, Cf, true) <= smem_doubles);
     const bool pre_ok = (int)blockIdx.x >= n_late;
     BS_T(0, f); BS_T(3, f);
-    // the factor (L, Linv) of every front below the top level was complete before the previous kernel started: the panel
-    // is pulled into shared memory while the parents are still solving; the boundary variable ids are immutable
+    // The factor (L, Linv) of every front below the top level was complete before the previous kernel started, so it is
+    // pulled into shared memory while the parents are still solving: the panel by ONE bulk asynchronous copy of the TMA
+    // engine (global -> shared, completion counted on an mbarrier; the panels start 16-byte aligned in the L arena), the
+    // small inverse diagonal blocks by ordinary loads.  The boundary variable ids are immutable.
+    __shared__ __align__(8) unsigned long long panel_bar;
+    const unsigned panel_bytes = (unsigned)(((size_t)Rf * Cf * sizeof(double)) & ~(size_t)15);
+    if (tid == 0 && staged) mbar_init(&panel_bar, 1);
+    __syncthreads();
     auto stage_factor = [&]() {
+        if (staged && tid == 0) tma_load_1d(sP, Lg, panel_bytes, &panel_bar);
         for (int i = tid; i < 81 * nbs; i += BS3_THREADS) sLi[i] = Linv[m.Ioff[f] + i];
-        if (staged)
-            for (int i = tid; i < Rf * Cf; i += BS3_THREADS) sP[i] = Lg[i];
     };
     if (pre_ok) stage_factor();
     int bvar[2] = {0, 0};              // this thread's boundary rows r = tid, tid + 512 -> index into D
@@ -644,7 +672,10 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     const int parent = chained ? m.parent[f] : -1;
     cudaGridDependencySynchronize();           // PDL: the kernel before (parents' solution / the factor) is complete
     cudaTriggerProgrammaticLaunchCompletion();
-    if (!force && !st->active) return;
+    if (!force && !st->active) {
+        if (staged && pre_ok) mbar_wait(&panel_bar, 0);     // never leave with a bulk copy into this CTA's shared memory in flight
+        return;
+    }
     int mine = 0;
     if (chained) {
         if (tid == 0) {
@@ -667,6 +698,11 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
     for (int r = tid + 2 * BS3_THREADS; r < Rb; r += BS3_THREADS) xb[r] = D[3 * (size_t)vars[npad + r / 3] + (r % 3)];
     if (!pre_ok) stage_factor();
     const double* Lp = staged ? sP : Lg;
+    if (staged) {
+        if (!mbar_wait(&panel_bar, 0))             // (never seen: the engine answers within microseconds)
+            for (int i = tid; i < Rf * Cf; i += BS3_THREADS) sP[i] = Lg[i];
+        if (tid == 0 && (((size_t)Rf * Cf) & 1)) sP[Rf * Cf - 1] = Lg[Rf * Cf - 1];     // an odd last double is not part of the bulk copy
+    }
     __syncthreads();
     // ts[c] = y[c] - sum_r L21[r,c] xb[r]      (one warp per column)
     for (int c = w; c < Cf; c += NW) {
