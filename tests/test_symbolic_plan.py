@@ -94,3 +94,44 @@ def test_invalid_graphs_are_rejected():
     self_loop = np.array([[1, 1]], dtype=np.int64)
     assert L.islam_plan_build(C.byref(h), 3, 1, self_loop.ctypes.data, None) < 0
     assert L.islam_plan_build(C.byref(h), 1, 0, None, None) < 0                      # fewer than two poses
+
+
+def _random_graph(seed):
+    """Random edge lists: sparse or dense bands, missing chain edges, duplicated and reversed edges, a few long edges."""
+    rng = np.random.default_rng(seed)
+    N = int(rng.integers(2, 70))
+    links = []
+    band = int(rng.integers(1, 6))
+    for k in range(1, band + 1):
+        for i in range(N - k):
+            if rng.random() < 0.7:
+                links.append((i, i + k) if rng.random() < 0.8 else (i + k, i))
+    for _ in range(int(rng.integers(0, 4))):                      # loop closures beyond band_max (default 16)
+        a, b = sorted(rng.integers(0, N, 2).tolist())
+        if b - a > 16:
+            links.append((a, b))
+    links += links[:int(rng.integers(0, 3))]                       # duplicates
+    links = np.array(links, dtype=np.int64).reshape(-1, 2)
+    gt, gv, _, _ = synth.ground_truth(N)
+    return synth._finish(f'rand{seed}', gt, gv, links, 0.1, rng, 3)
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_random_graphs_plan_solves_like_dense(seed):
+    """Property test of the ordering / trimming / push maps on arbitrary structures (not only the band patterns above)."""
+    g = _random_graph(seed)
+    lm = po.SparseLM(g, np.float64, solver='splu')
+    H, gg, _, _ = lm.assemble(lm._res())
+    H = H.toarray()
+    opts = [{}, {'leaf_max': 2, 'pivot_max': 1}, {'n_parts': 2}, {'band_max': 2}][seed % 4]
+    plan = mf_emul.get_plan(g.N, g.links, **opts)
+    piv = np.concatenate([plan['vars'][plan['vars_off'][f]:plan['vars_off'][f] + plan['np'][f]] for f in range(plan['F'])])
+    assert sorted(piv.tolist()) == list(range(3 * g.N))
+    Hd, Ho = mf_emul.blocks_from_dense(H, plan, g.N)
+    scale = 1.0 + 1e-4
+    D = mf_emul.solve(plan, Hd, Ho, gg, scale)
+    A = H.copy()
+    d = np.clip(np.diag(A), 1e-4, 1e32) * scale
+    A[np.arange(len(d)), np.arange(len(d))] = d
+    Dref = np.linalg.solve(A, -gg.reshape(-1)).reshape(-1, 9)
+    assert np.abs(D - Dref).max() <= 1e-8 * max(np.abs(Dref).max(), 1e-12)
