@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LM_ITERS = 10                 # optimizer.step calls per step (StopOnPlateau's max steps, pvgo.py:172)
+WORKLOAD = ('C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows; '
+            f'{LM_ITERS} fixed LM iterations per step, loss_weight (1,0.1,10,0.1), radius 1e4')
 SURVEY_BYTES_PER_ITER = 62e6  # SURVEY.md 8d compact fp32 byte model of one LM iteration @C2
 SURVEY_BYTES_FACTOR = 21.6e6  # read H (7.7 MB) + write L (13.9 MB): the factorisation's share of the above
 
@@ -111,32 +113,62 @@ def time_oracle(g, iters, dtype=np.float64):
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU port of the path (oracle.SparseLM; PyPose itself is absent) on the box's host
+    cores, on the SAME config as our arm: every step is LM_ITERS optimizer.step calls on C2 from the same initial guess."""
     if rank != 0:
         return
     g = _graph()
-    sample_iters = 2
     for _ in range(min(args.warmup, 1)):
         time_oracle(g, 1)
     t = 0.0
     for _ in range(args.steps):
-        dt, _lm = time_oracle(g, sample_iters)
+        dt, _lm = time_oracle(g, LM_ITERS)
         t += dt
-    its = sample_iters * args.steps / t
+    its = LM_ITERS * args.steps / t
     cores = _cpu_threads()
     out = {
         'impl': 'reference', 'metric': 'LM iterations/s on the 5k-pose PVGO (C2)', 'value': its, 'unit': 'LM it/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'factors_per_s': its * g.factors,
-        'config': {'workload': 'C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows',
-                   'parallelism': 'host CPU'},
-        'cpu_baseline': {'value': its, 'unit': 'LM it/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{sample_iters} LM iterations of C2 per step (oracle.SparseLM float64: NumPy assembly + '
+        'factors_per_s': its * g.factors, 'residual_rows_per_s': its * g.rows,
+        'config': {'workload': WORKLOAD, 'parallelism': 'host CPU'},
+        'cpu_baseline': {'value': its, 'unit': 'LM it/s', 'factors_per_s': its * g.factors, 'cores': cores, 'kind': 'port',
+                         'sample': f'{LM_ITERS} LM iterations of C2 per step x {args.steps} steps (oracle.SparseLM float64: NumPy assembly + '
                                    f'LAPACK banded Cholesky; PyPose itself is absent and its dense algorithm needs 324 GB at C2)'},
         'e2e': {'value': its, 'unit': 'LM it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     _emit(out)
+
+
+def _pose_error_vs_fixture(nodes, vels=None):
+    """Parity carried by the bench line: relative pose error (after align_to, pvgo.py:195) against the float64 CPU oracle's
+    solution of the same graph after the same 10 iterations (tests/golden/c2_oracle_final.npz, made by make_c2_golden.py).
+    `nodes` are already aligned.  Same definition as the parity tests: ||X - Xref||_F / ||Xref||_F on the 7-vector storage
+    with the quaternion sign made canonical (w >= 0)."""
+    p = os.path.join(ROOT, 'tests', 'golden', 'c2_oracle_final.npz')
+    if not os.path.exists(p):
+        return None
+    fx = np.load(p)
+    ref = fx['nodes'].astype(np.float64).copy()
+    a = np.asarray(nodes, np.float64).copy()
+    for x in (a, ref):
+        x[:, 3:] = np.where(x[:, 6:7] < 0, -x[:, 3:], x[:, 3:])
+    out = {'rel': float(np.linalg.norm(a - ref) / np.linalg.norm(ref)),
+           'max_trans_m': float(np.max(np.linalg.norm(a[:, :3] - ref[:, :3], axis=1))),
+           'gate': 1e-5, 'fixture': 'tests/golden/c2_oracle_final.npz (float64 CPU oracle, same 10 steps, aligned)'}
+    if vels is not None:
+        out['max_vel_mps'] = float(np.max(np.abs(np.asarray(vels, np.float64) - fx['vels'])))
+    return out
+
+
+def _align_np(nodes, vels, target):
+    """align_to (pvgo.py:114-119) on host arrays, for the sharded runs whose gathered state comes back unaligned."""
+    from islam_b200 import synth
+    n, v, t = np.asarray(nodes, np.float64), np.asarray(vels, np.float64), np.asarray(target, np.float64)
+    T = synth._se3_mul(t, synth._se3_inv(n[0]))
+    q = synth._qmul(t[3:], synth._qinv(n[0, 3:]))
+    return synth._se3_mul(T[None], n), synth._qrot(q[None], v)
 
 
 # ---------------------------------------------------------------------------------------------------- our arm
@@ -196,6 +228,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # parity of THIS run's result (the state the last timed step left behind), after align_to
+    if sharded:
+        n_fin, v_fin = sh.get_state()
+        n_al, v_al = _align_np(n_fin.cpu().numpy(), v_fin.cpu().numpy(), g.init_nodes[0])
+    else:
+        n_al, v_al = s.align(nodes0[0])
+        n_al, v_al = n_al.cpu().numpy(), v_al.cpu().numpy()
+    pose_err = _pose_error_vs_fixture(n_al, v_al)
     iters_total = LM_ITERS * args.steps                  # one graph, however many GPUs share it
     value = iters_total / (ms * 1e-3)
     launches = tries * (7 + s.dims.levels + s.dims.bs_launches)   # begin_try, factors, assemble, begin_step, one factor launch per level, back-substitution (top levels chained in one launch), retract, trial factors, end_try
@@ -223,10 +263,14 @@ def run_ours(args, rank, world, local_rank):
                     'peak_source': peak_src, 'algorithmic_bytes_per_factorisation': SURVEY_BYTES_FACTOR,
                     'avg_launch_us': per_launch_s * 1e6,
                     'phases_ms': {k: float(np.mean([p[k] for p in ph])) for k in ph[0]}, 'whole_iteration': whole}
+    # `traffic` cannot be measured live (DRAM byte counters need ncu): it is the per-launch dram__bytes of the committed
+    # `ncu --set full` capture of this same command (profiles/traffic.json names the capture); stated as such in the line
     tr = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tr) and not sharded:
         try:
-            roofline['traffic'] = json.load(open(tr)).get('k_factor_level_bytes_per_launch')
+            tj = json.load(open(tr))
+            roofline['traffic'] = tj.get('k_factor_level_bytes_per_launch')
+            roofline['traffic_source'] = 'ncu-derived, not live: ' + str(tj.get('source', 'profiles/traffic.json'))
         except Exception:
             pass
 
@@ -274,8 +318,7 @@ def run_ours(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 residuals/Jacobians, f64 normal equations + Cholesky',
         'data': 'synthetic', 'factors_per_s': value * F, 'residual_rows_per_s': value * g.rows,
-        'config': {'workload': 'C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows; '
-                               f'{LM_ITERS} fixed LM iterations per step, loss_weight (1,0.1,10,0.1), radius 1e4',
+        'config': {'workload': WORKLOAD,
                    'parallelism': 'single GPU' if world == 1 else
                    f'{world} contiguous pose windows of ONE C2 graph; per LM try one NCCL all-reduce of the shared separator panels '
                    f'({s.dims.n_shared_fronts} fronts, {s.dims.shared_doubles * 8 / 1e6:.2f} MB); the trial sums travel through NVLink peer mailboxes inside the kernel that closes the try',
@@ -283,11 +326,12 @@ def run_ours(args, rank, world, local_rank):
                                     f'(L {d.L_doubles * 8 / 1e6:.0f} MB + U {d.U_doubles * 8 / 1e6:.0f} MB + destination maps {d.U_doubles * 2 / 1e6:.0f} MB + '
                                     f'J^T W J blocks {648 * (d.N + d.P) / 1e6:.0f} MB + per-factor products {336 * d.E / 1e6:.0f} MB), more than the 126 MB L2')(s.dims)},
         'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
-        'lm': {'final_loss': st.loss, 'steps_done': st.steps_done, 'tries': st.tries_total, 'info': st.info},
+        'lm': {'final_loss': st.loss, 'steps_done': st.steps_done, 'tries': st.tries_total, 'info': st.info,
+               'rel_pose_error_vs_oracle': pose_err},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t_cpu, _ = time_oracle(g, 10)
-        out['cpu_baseline'] = {'value': 10 / t_cpu, 'unit': 'LM it/s', 'cores': _cpu_threads(), 'kind': 'port',
+        out['cpu_baseline'] = {'value': 10 / t_cpu, 'unit': 'LM it/s', 'factors_per_s': 10 / t_cpu * F, 'cores': _cpu_threads(), 'kind': 'port',
                                'sample': '10 LM iterations of C2 (oracle.SparseLM float64: single-threaded NumPy assembly + LAPACK banded '
                                          'Cholesky on the BLAS thread pool, same normal equations; literal dense PyPose needs 324 GB at C2)'}
     if rank == 0:

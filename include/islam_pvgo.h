@@ -21,6 +21,9 @@
  *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.  islam_pvgo_create: -2 bad edge list,
  *     -5 boundary too wide for the back-substitution kernel, -6 dense loop-closure root with n_parts > 1 (the dense
  *     root is single-GPU), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
+ *     islam_pvgo_lm_step / _lm_run: -9 the step / loop did not close within its worst-case try budget.
+ *     LM state `info`: 1 Cholesky failed (PyPose's "Linear solver failed"), 2 a multi-GPU peer never answered, 3 a device-side
+ *     wait inside the back-substitution timed out (wedged device); 2 and 3 also clear `continual`.
  *   - Numerical failure of the Cholesky (non-positive pivot / NaN) does not abort: it raises `info` in the
  *     LM state, and the step is abandoned exactly as PyPose's "Linear solver failed. Breaking..." path.
  *   - A handle is not thread-safe; use one per host thread / stream.
@@ -158,7 +161,13 @@ int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host);
  * trans_loss/rot_loss (E); if grad_* given: d loss_e / d(left tangent of P_e) (E x 6 each) */
 int islam_pvgo_vo_loss(islam_pvgo* h, const float* P, float* trans_loss, float* rot_loss,
                        float* grad_trans /* nullable */, float* grad_rot /* nullable */, void* stream);
-int islam_pvgo_imu_loss(islam_pvgo* h, float* trans_loss /* M */, float* rot_loss /* M */, void* stream);
+/* imu_loss (pvgo.py:95-111) at the current nodes / velocities for the given IMU measurements (NULL: the ones stored by
+ * set_problem): trans_loss = |dv - diff(v)|^2, rot_loss = |Log(dR^-1 R_i^-1 R_{i+1})|^2 per pair (M).  grad_*: nullable,
+ * M x 3 each: d rot_loss / d(left tangent of dR), d trans_loss / d(dv)  (pvgo.py:149-150,188-189: the loss back-propagates
+ * into the IMU model through imu_drots / imu_dvels) */
+int islam_pvgo_imu_loss(islam_pvgo* h, const float* imu_drots /* M x 4, nullable */, const float* imu_dvels /* M x 3, nullable */,
+                        float* trans_loss /* M */, float* rot_loss /* M */, float* grad_drots /* nullable */,
+                        float* grad_dvels /* nullable */, void* stream);
 /* align_to (pvgo.py:114-119): nodes <- T X0^-1 nodes, vels <- R_T R0^-1 vels; target: 7 floats on device */
 int islam_pvgo_align(islam_pvgo* h, const float* target, float* nodes_out, float* vels_out, void* stream);
 
@@ -176,11 +185,14 @@ int64_t islam_imu_workspace_bytes(int32_t S, int32_t K);
 /* One fused pass over a batch of B samples (the reference loops over samples in Python).  disp B x H x W (or NULL when
  * depth is given), flow B x 2 x H x W, motion B x 7 (SE3, frame k -> k+1 as TartanVO reports it), intr B x 4 (fx, fy, cx, cy),
  * baseline B, depth B x H x W or NULL, mask_in B x H x W bytes or NULL (the Canny edge mask), disp_th B.
- * Outputs: scale B, z B x H x W, mask / depth_mask B x H x W bytes, mask_count B (nullable; the reference warns below 500). */
+ * Outputs: scale B, z B x H x W, mask / depth_mask B x H x W bytes, mask_count B (nullable; the reference warns below 500).
+ * grad_sums (nullable, B x 11 float64): what the backward pass of s = num / den into `motion` needs, reduced in the same pass:
+ * {num, den, d num / d a (3), d den / d a (3), d num / d(left tangent of R = T.Inv().rotation()) (3)}, a = K normalize(t_inv). */
 int islam_scale_from_disp_flow(const float* disp, const float* flow, const float* motion, const float* intr,
                                const float* baseline, const float* depth, const uint8_t* mask_in, const float* disp_th,
                                int32_t B, int32_t H, int32_t W, float* scale, float* z, uint8_t* mask, uint8_t* depth_mask,
-                               int32_t* mask_count, void* workspace /* islam_scale_workspace_bytes(B,H,W) */, void* stream);
+                               int32_t* mask_count, double* grad_sums, void* workspace /* islam_scale_workspace_bytes(B,H,W) */,
+                               void* stream);
 int64_t islam_scale_workspace_bytes(int32_t B, int32_t H, int32_t W);
 
 /* ---- elementwise LieTensor maps (forward + left-tangent backward), n elements ------------------------- */

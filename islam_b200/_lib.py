@@ -74,12 +74,12 @@ _SIGS = {
     'islam_pvgo_mailbox_export': (C.c_int, [_P, _P]),
     'islam_pvgo_mailbox_connect': (C.c_int, [_P, _P]),
     'islam_pvgo_vo_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
-    'islam_pvgo_imu_loss': (C.c_int, [_P, _P, _P, _P]),
+    'islam_pvgo_imu_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'islam_pvgo_align': (C.c_int, [_P, _P, _P, _P, _P]),
     'islam_imu_preintegrate': (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_float, C.c_int32, _P, _P, _P,
                                          _P, _P]),
     'islam_imu_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
-    'islam_scale_from_disp_flow': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    'islam_scale_from_disp_flow': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     'islam_scale_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     'islam_lie_exp': (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),
     'islam_lie_log': (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P]),

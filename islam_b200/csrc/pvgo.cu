@@ -80,10 +80,14 @@ k_vo_loss(const LMState* __restrict__ st, const float* __restrict__ nodes0, cons
     }
 }
 
+// imu_loss (pvgo.py:95-111) at the current state for the given (or the stored) IMU measurements.  g_drot / g_dvel:
+// d(rot_loss_i) / d(left tangent of dR_i) = -2 (Jl^-1(e) R(dR)^T)^T e  and  d(trans_loss_i) / d(dv_i) = 2 adjvelerr_i,
+// the way PyPose's LieTensor backward reports them (left tangent; the caller pads it to the 4-slot embedding, A.1).
 __global__ void __launch_bounds__(128)
 k_imu_loss(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
            const float* __restrict__ vels0, const float* __restrict__ vels1, const float* __restrict__ drot,
-           const float* __restrict__ dvel, int M, float* __restrict__ tl, float* __restrict__ rl) {
+           const float* __restrict__ dvel, int M, float* __restrict__ tl, float* __restrict__ rl,
+           float* __restrict__ g_drot, float* __restrict__ g_dvel) {
     const float* nodes = st->cur ? nodes1 : nodes0;
     const float* vels = st->cur ? vels1 : vels0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,14 +96,29 @@ k_imu_loss(const LMState* __restrict__ st, const float* __restrict__ nodes0, con
 #pragma unroll
     for (int k = 0; k < 4; ++k) { dq[k] = drot[4 * (size_t)i + k]; qa[k] = nodes[7 * (size_t)i + 3 + k]; qb[k] = nodes[7 * (size_t)(i + 1) + 3 + k]; }
     rot_factor(qa, qb, dq, r, nullptr);
-    float t = 0.f;
+    float t = 0.f, a[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float a = dvel[3 * (size_t)i + k] - (vels[3 * (size_t)(i + 1) + k] - vels[3 * (size_t)i + k]);
-        t += a * a;
+        a[k] = dvel[3 * (size_t)i + k] - (vels[3 * (size_t)(i + 1) + k] - vels[3 * (size_t)i + k]);
+        t += a[k] * a[k];
     }
     tl[i] = t;
     rl[i] = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    if (g_dvel != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g_dvel[3 * (size_t)i + k] = 2.f * a[k];
+    }
+    if (g_drot != nullptr) {
+        // e = Log(dR^-1 A): dR <- Exp(d) dR gives e' ~ e - Jl^-1(e) R(dR^-1) d
+        float Ji[9], dqi[4], R[9], J[9];
+        so3_Jl_inv(r, Ji);
+        q_inv(dq, dqi);
+        q_matrix(dqi, R);
+        mat3_mul(Ji, R, J);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            g_drot[3 * (size_t)i + k] = -2.f * (J[k] * r[0] + J[3 + k] * r[1] + J[6 + k] * r[2]);
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -950,6 +969,7 @@ extern "C" int islam_pvgo_lm_step(islam_pvgo* h, islam_lm_state* out, void* stre
         if (h->st_host->steps_done >= target) break;
     }
     if (out) *out = *h->st_host;
+    if (h->st_host->steps_done < target && !h->st_host->info) return -9;     // guard exhausted: the step never closed
     return 0;
 }
 
@@ -961,7 +981,10 @@ extern "C" int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out, void* strea
     // Fixed step count: exactly max_steps accepted tries are coming, + 2 for rejected ones.  With the plateau scheduler the
     // loop usually stops after a few steps (9-pose windows of train.py: 2-4), so go in rounds of 4.
     int budget = h->prm.use_scheduler ? std::min(h->prm.max_steps + 2, 4) : h->prm.max_steps + 2;
-    for (int guard = 0; guard < 64; ++guard) {
+    // worst case every step burns `reject` rolled-back tries before it closes
+    const long long worst = (long long)std::max(1, h->prm.max_steps) * (std::max(0, h->prm.reject) + 1);
+    const int rounds = (int)std::min<long long>(64 + worst / 4, 1 << 20);
+    for (int guard = 0; guard < rounds; ++guard) {
         for (int k = 0; k < budget; ++k) {
             int rc = graph_try(h, s);
             if (rc) return rc;
@@ -972,6 +995,7 @@ extern "C" int islam_pvgo_lm_run(islam_pvgo* h, islam_lm_state* out, void* strea
         budget = 4;
     }
     if (out) *out = *h->st_host;
+    if (h->st_host->continual) return -9;         // the loop never ended within its worst-case budget: reported, never silent
     return 0;
 }
 
@@ -993,11 +1017,13 @@ extern "C" int islam_pvgo_vo_loss(islam_pvgo* h, const float* P, float* tl, floa
     return (int)cudaGetLastError();
 }
 
-extern "C" int islam_pvgo_imu_loss(islam_pvgo* h, float* tl, float* rl, void* stream) {
+extern "C" int islam_pvgo_imu_loss(islam_pvgo* h, const float* drots, const float* dvels, float* tl, float* rl,
+                                   float* g_drots, float* g_dvels, void* stream) {
     if (!h || !tl || !rl) return -1;
     const Plan& p = h->plan;
     k_imu_loss<<<(p.M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
-                                                                   h->vels[1].p, h->drot.p, h->dvel.p, p.M, tl, rl);
+                                                                   h->vels[1].p, drots ? drots : h->drot.p,
+                                                                   dvels ? dvels : h->dvel.p, p.M, tl, rl, g_drots, g_dvels);
     return (int)cudaGetLastError();
 }
 

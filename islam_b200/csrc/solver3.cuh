@@ -682,8 +682,12 @@ k_backsolve3(const LMState* __restrict__ st, const int* __restrict__ fronts, Fro
             mine = *(volatile int*)(count + f);
             if (parent >= 0 && parent != dense_root) {
                 const long long t0 = clock64();            // the parent is co-resident and earlier in the grid; the bound
-                while (*(volatile int*)(count + parent) != mine + 1)          // only guards against a wedged device
-                    if (clock64() - t0 > (1LL << 31)) break;
+                while (*(volatile int*)(count + parent) != mine + 1)          // only guards against a wedged device:
+                    if (clock64() - t0 > (1LL << 31)) {                       // report it (info = 3) and stop the LM loop
+                        LMState* sw = const_cast<LMState*>(st);
+                        sw->info = 3; sw->continual = 0;
+                        break;
+                    }
             }
             __threadfence();
         }

@@ -12,6 +12,48 @@ from ._lib import IslamError
 from .pvgo import _plain
 
 
+def _quat_rot(q, p):
+    v, w = q[..., :3], q[..., 3:4]
+    t = 2.0 * torch.linalg.cross(v, p)
+    return p + w * t + torch.linalg.cross(v, t)
+
+
+class _ScaleFn(torch.autograd.Function):
+    """s = sum(M w) / sum(M M) with autograd into `motion` (dense_ba.py:144-166 runs with grad enabled at TartanVO.py:92, and
+    TartanVO.py:181 feeds the scale back into the pose).  The per-pixel sums of the backward pass come out of the SAME fused
+    kernel pass as the value (grad_sums, include/islam_pvgo.h); what remains here is the 7-number chain rule per sample, in
+    PyPose's convention: T.Inv() is a LieTensor op (left-tangent gradient, -Ad(T^-1)^T), .rotation() keeps the tangent,
+    .translation() is a plain slice whose raw gradient lands in the tau slots."""
+
+    @staticmethod
+    def forward(ctx, motion, call):
+        scale, sums = call(motion.detach(), True)
+        ctx.save_for_backward(motion.detach(), sums)
+        ctx.intr = call.intr
+        return scale
+
+    @staticmethod
+    def backward(ctx, g_s):
+        mo, sums = ctx.saved_tensors
+        mo = mo.double()
+        fx, fy, cx, cy = (ctx.intr[:, k].double() for k in range(4))
+        num, den = sums[:, 0], sums[:, 1]
+        s = num / den
+        ds_da = (sums[:, 2:5] - s.unsqueeze(-1) * sums[:, 5:8]) / den.unsqueeze(-1)
+        ds_dr = sums[:, 8:11] / den.unsqueeze(-1)
+        t, q = mo[:, :3], mo[:, 3:7]
+        qi = q * torch.tensor([-1.0, -1.0, -1.0, 1.0], dtype=q.dtype, device=q.device)
+        t_inv = -_quat_rot(qi, t)
+        nrm = t_inv.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        n = t_inv / nrm
+        ds_dn = torch.stack([fx * ds_da[:, 0], fy * ds_da[:, 1], cx * ds_da[:, 0] + cy * ds_da[:, 1] + ds_da[:, 2]], dim=1)
+        g_tau = (ds_dn - n * (n * ds_dn).sum(1, keepdim=True)) / nrm          # raw gradient w.r.t. T.Inv().translation()
+        # Y = T^-1: grad_T = -Ad(T^-1)^T [g_tau; g_phi] = -[R g_tau ; R (g_phi - t_inv x g_tau)]
+        g6 = -torch.cat([_quat_rot(q, g_tau), _quat_rot(q, ds_dr - torch.linalg.cross(t_inv, g_tau))], dim=1)
+        g7 = torch.cat([g6, torch.zeros_like(g6[:, :1])], dim=1) * g_s.double().reshape(-1, 1)
+        return g7.to(torch.float32), None
+
+
 def _f(t, dev, shape=None):
     t = _plain(t).detach().to(device=dev, dtype=torch.float32).contiguous()
     if shape is not None and tuple(t.shape) != tuple(shape):
@@ -22,7 +64,8 @@ def _f(t, dev, shape=None):
 def scale_from_disp_flow_batch(disp, flow, motion, intrinsics, baseline, depth=None, mask=None, disp_th=1.0, device=None):
     """disp (B,H,W) [ignored when depth is given], flow (B,2,H,W), motion (B,7) SE3, intrinsics (B,4) = fx,fy,cx,cy,
     baseline (B,), depth (B,H,W) | None, mask (B,H,W) bool | None, disp_th float | (B,).
-    Returns scale (B,), z (B,H,W), mask (B,H,W) bool, depth_mask (B,H,W) bool, mask_count (B,) int32 — on the device."""
+    Returns scale (B,), z (B,H,W), mask (B,H,W) bool, depth_mask (B,H,W) bool, mask_count (B,) int32 — on the device.
+    `scale` carries autograd history into `motion` when that requires grad (as the reference's does)."""
     flow_t = _plain(flow)
     dev = torch.device(device) if device is not None else (flow_t.device if flow_t.is_cuda else torch.device('cuda', torch.cuda.current_device()))
     if dev.type != 'cuda':
@@ -31,13 +74,13 @@ def scale_from_disp_flow_batch(disp, flow, motion, intrinsics, baseline, depth=N
     B, two, H, W = flow_t.shape
     if two != 2:
         raise IslamError('flow must be (B, 2, H, W)')
-    mo = _f(motion, dev)
-    if mo.shape[-1] == 6:                       # dense_ba.py:92-95: an se3 input goes through Exp first
+    mo_in = _plain(motion)
+    if mo_in.shape[-1] == 6:                    # dense_ba.py:92-95: an se3 input goes through Exp first (differentiable)
         from .pypose_compat import _ops
-        mo = _ops.ExpFn.apply(mo, _ops.SE3)
-    elif mo.shape[-1] != 7:
+        mo_in = _ops.ExpFn.apply(mo_in.to(device=dev, dtype=torch.float32), _ops.SE3)
+    elif mo_in.shape[-1] != 7:
         raise IslamError('motion must be SE3 (7 numbers) or se3 (6 numbers)')
-    mo = mo.reshape(B, 7).contiguous()
+    mo_in = mo_in.to(device=dev, dtype=torch.float32).reshape(B, 7)
     intr = _f(intrinsics, dev, (B, 4))
     bl = _f(torch.as_tensor(baseline).reshape(-1), dev, (B,))
     th = torch.as_tensor(disp_th, dtype=torch.float32).reshape(-1)
@@ -49,16 +92,27 @@ def scale_from_disp_flow_batch(disp, flow, motion, intrinsics, baseline, depth=N
         raise IslamError(f'expected mask shape {(B, H, W)}, got {tuple(m_in.shape)}')
     L = _lib.lib()
     ws = torch.empty(int(L.islam_scale_workspace_bytes(B, H, W)), dtype=torch.uint8, device=dev)
-    scale = torch.empty(B, dtype=torch.float32, device=dev)
     z = torch.empty(B, H, W, dtype=torch.float32, device=dev)
     m_out = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
     dm_out = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
     cnt = torch.empty(B, dtype=torch.int32, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-    with torch.cuda.device(dev):
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(L.islam_scale_from_disp_flow(p(d), p(flow_t), p(mo), p(intr), p(bl), p(dep), p(m_in), p(th), B, H, W, p(scale), p(z),
-                                                p(m_out), p(dm_out), p(cnt), p(ws), st), 'islam_scale_from_disp_flow')
+
+    def call(mo, want_grad):
+        mo = mo.contiguous()
+        scale = torch.empty(B, dtype=torch.float32, device=dev)
+        sums = torch.empty(B, 11, dtype=torch.float64, device=dev) if want_grad else None
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.islam_scale_from_disp_flow(p(d), p(flow_t), p(mo), p(intr), p(bl), p(dep), p(m_in), p(th), B, H, W, p(scale),
+                                                    p(z), p(m_out), p(dm_out), p(cnt), p(sums), p(ws), st), 'islam_scale_from_disp_flow')
+        return (scale, sums) if want_grad else scale
+    call.intr = intr
+
+    if mo_in.requires_grad and torch.is_grad_enabled():
+        scale = _ScaleFn.apply(mo_in, call)
+    else:
+        scale = call(mo_in.detach(), False)
     return scale, z, m_out.bool(), dm_out.bool(), cnt
 
 

@@ -30,7 +30,11 @@ def prase_init(init=None, motion_mode=False, device='cuda:0'):
     else:
         pos, vel = torch.zeros(3, dtype=dtype), torch.zeros(3, dtype=dtype)
         rot = torch.tensor([0., 0., 0., 1.], dtype=dtype)
-    return pos.to(device), rot.to(device), vel.to(device)
+    return pos.to(device), _wrap_so3(rot.to(device)), vel.to(device)
+
+
+def _plain(t):
+    return t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
 
 
 def _to_np(x):
@@ -91,7 +95,7 @@ class IMUModule:
                 gyr = gyr - self.gyro_bias.view(1, 3)
         acc, gyr, dts = acc.contiguous(), gyr.contiguous(), dts.contiguous()
         off = (self._sync[st:end + 1] - b0).contiguous()
-        init10 = torch.cat([init_pos, init_rot, init_vel]).to(torch.float32).contiguous()
+        init10 = torch.cat([init_pos, _plain(init_rot), init_vel]).to(torch.float32).contiguous()
         pos = torch.empty(K, 3, device=self.device)
         rot = torch.empty(K, 4, device=self.device)
         vel = torch.empty(K, 3, device=self.device)
@@ -106,6 +110,11 @@ class IMUModule:
             t.record_stream(self.stream)
         if not motion_mode:                                                                          # :86-89
             pos = torch.cat([init_pos.view(1, 3).float(), pos])
-            rot = torch.cat([init_rot.view(1, 4).float(), rot])
+            rot = torch.cat([_plain(init_rot).view(1, 4).float(), rot])
             vel = torch.cat([init_vel.view(1, 3).float(), vel])
-        return pos.cpu(), _wrap_so3(rot.cpu()), [], vel.cpu()
+        # poses.cpu(), rots.cpu(), vels.cpu() (imu_integrator.py:148-164) as ONE packed copy into pinned memory and one sync
+        packed = torch.cat([pos, rot, vel], dim=1)
+        host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host[:, 0:3].clone(), _wrap_so3(host[:, 3:7].clone()), [], host[:, 7:10].clone()

@@ -19,8 +19,8 @@ import torch
 from ._lib import IslamError
 from .solver import PVGOSolver
 
-_SOLVER_CACHE = {}
-_CACHE_MAX = 8
+_SOLVER_POOL = {}          # structural key -> idle PVGOSolver handles (symbolic plan + device workspace)
+_POOL_MAX = 8
 
 
 def _plain(t):
@@ -41,8 +41,15 @@ def _wrap_like(ref, data, ltype_name):
     return data
 
 
-def get_solver(N, links, device):
-    links_np = np.ascontiguousarray(_plain(links).detach().cpu().numpy(), dtype=np.int64).reshape(-1, 2)
+def _links_np(links):
+    return np.ascontiguousarray(_plain(links).detach().cpu().numpy(), dtype=np.int64).reshape(-1, 2)
+
+
+def acquire_solver(N, links, device):
+    """Check a solver for this graph structure OUT of the pool (the symbolic analysis is what is expensive and is reused);
+    a handle is owned by exactly one PoseVelGraph at a time, so two live graphs never share device state.
+    release_solver() hands it back."""
+    links_np = _links_np(links)
     dev = torch.device(device)
     if dev.type == 'cuda' and dev.index is None:
         dev = torch.device('cuda', torch.cuda.current_device())
@@ -50,15 +57,28 @@ def get_solver(N, links, device):
     # a cryptographic hash of the edge list cost ~0.6 ms per run_pvgo call at 40 000 edges
     flat = links_np.reshape(-1)
     key = (int(N), str(dev), links_np.shape[0], int(flat.sum()), int(flat[::3].sum()), int(flat[1::5].sum()))
-    s = _SOLVER_CACHE.get(key)
-    if s is not None and not np.array_equal(s.links, links_np):
-        s = None
-    if s is None:
-        if len(_SOLVER_CACHE) >= _CACHE_MAX:
-            _SOLVER_CACHE.pop(next(iter(_SOLVER_CACHE)))
-        s = PVGOSolver(N, links_np, device=dev)
-        _SOLVER_CACHE[key] = s
+    idle = _SOLVER_POOL.get(key, [])
+    for k, s in enumerate(idle):
+        if np.array_equal(s.links, links_np):
+            idle.pop(k)
+            s._pool_key = key
+            return s
+    s = PVGOSolver(N, links_np, device=dev)
+    s._pool_key = key
     return s
+
+
+def release_solver(s):
+    key = getattr(s, '_pool_key', None)
+    if key is None:
+        return
+    if sum(len(v) for v in _SOLVER_POOL.values()) >= _POOL_MAX:       # evict the oldest idle handle
+        for k in list(_SOLVER_POOL):
+            if _SOLVER_POOL[k]:
+                _SOLVER_POOL[k].pop(0)
+                break
+            del _SOLVER_POOL[k]
+    _SOLVER_POOL.setdefault(key, []).append(s)
 
 
 class _VoLoss(torch.autograd.Function):
@@ -81,35 +101,76 @@ class _VoLoss(torch.autograd.Function):
         return g.to(ctx.dev), None
 
 
+class _ImuLoss(torch.autograd.Function):
+    """imu_loss (pvgo.py:95-111) evaluated on the caller's (possibly grad-carrying) imu_drots / imu_dvels
+    (pvgo.py:149-150,188-189).  Gradients: d trans_loss / d dv = 2 adjvelerr; d rot_loss / d dR in PyPose's convention
+    (left tangent, padded to the 4-slot SO3 embedding)."""
+
+    @staticmethod
+    def forward(ctx, drots, dvels, solver):
+        tl, rl, gr, gv = solver.imu_loss(drots, dvels, with_grad=True)
+        ctx.save_for_backward(gr, gv)
+        ctx.devs = (drots.device, dvels.device)
+        return tl, rl
+
+    @staticmethod
+    def backward(ctx, g_tl, g_rl):
+        gr, gv = ctx.saved_tensors
+        g_r = g_rl.to(gr.device).unsqueeze(-1) * gr
+        g_r = torch.cat([g_r, torch.zeros_like(g_r[:, :1])], dim=1)
+        g_v = g_tl.to(gv.device).unsqueeze(-1) * gv
+        return g_r.to(ctx.devs[0]), g_v.to(ctx.devs[1]), None
+
+
 class PoseVelGraph(torch.nn.Module):
-    """pvgo.py:15-119.  Parameters live in the solver handle on the GPU (float32, as the reference)."""
+    """pvgo.py:15-119.  Parameters live in the solver handle on the GPU (float32, as the reference).  The handle is checked
+    out of a pool for the lifetime of the graph, so every live graph has its own device state."""
 
     def __init__(self, nodes, vels, reproj=None, links=None, device='cuda:0'):
         super().__init__()
-        if reproj is not None:
-            raise NotImplementedError('the optional reprojection factor (pvgo.py:53-61) is not on the B200 path yet')
         nodes_t, vels_t = _plain(nodes).detach(), _plain(vels).detach()
         assert nodes_t.size(0) == vels_t.size(0)                              # pvgo.py:19
         self._device = torch.device(device)
         self._init = (nodes_t, vels_t)
         self._nodes_ref = nodes
+        self.reproj = reproj
         self.solver = None
-        self._problem_key = None
+        self._links_obj = None
         if links is not None:
             self._bind(links)
 
+    def __del__(self):
+        s, self.solver = getattr(self, 'solver', None), None
+        if s is not None:
+            try:
+                release_solver(s)
+            except Exception:      # interpreter shutdown
+                pass
+
     def _bind(self, links):
-        self.solver = get_solver(self._init[0].size(0), links, self._device)
+        self.solver = acquire_solver(self._init[0].size(0), links, self._device)
+        self._links_obj = links
         self.solver.set_state(*self._init)
 
+    def _check_edges(self, edges):
+        """The graph structure is fixed at construction; a different edge list is an error, not silently ignored."""
+        if edges is None or edges is self._links_obj:
+            return
+        if not np.array_equal(_links_np(edges), self.solver.links):
+            raise IslamError('this PoseVelGraph was built for a different edge list; construct a new graph')
+        self._links_obj = edges
+
     def _ensure(self, edges, poses, imu_drots, imu_dtrans, imu_dvels, dts, loss_weight=None):
+        """Stage the measurements of THIS call (the reference module is stateless w.r.t. its inputs, pvgo.py:26)."""
         if self.solver is None:
             self._bind(edges)
-        if loss_weight is not None or self._problem_key is None:
-            lw = (1, 1, 1, 1) if loss_weight is None else loss_weight
-            self.solver.set_problem(_plain(poses), _plain(imu_drots), _plain(imu_dtrans), _plain(imu_dvels),
-                                    _plain(dts).reshape(-1), lw)
-            self._problem_key = tuple(float(x) for x in lw)
+        else:
+            self._check_edges(edges)
+        if loss_weight is not None:
+            self._loss_weight = tuple(float(x) for x in loss_weight)
+        lw = getattr(self, '_loss_weight', (1.0, 1.0, 1.0, 1.0))
+        self.solver.set_problem(_plain(poses), _plain(imu_drots), _plain(imu_dtrans), _plain(imu_dvels),
+                                _plain(dts).reshape(-1), lw, reproj=self.reproj)
 
     @property
     def nodes(self):
@@ -121,19 +182,26 @@ class PoseVelGraph(torch.nn.Module):
         return self.solver.get_state()[1]
 
     def forward(self, edges, poses, imu_drots, imu_dtrans, imu_dvels, dts):
-        """Returns (pgerr, adjvelerr, imuroterr, transvelerr) — pvgo.py:64."""
+        """Returns (pgerr, adjvelerr, imuroterr, transvelerr[, reprojerr]) — pvgo.py:61-64."""
         self._ensure(edges, poses, imu_drots, imu_dtrans, imu_dvels, dts)
         self.solver.linearize()
         return self.solver.residuals()
 
     def vo_loss(self, edges, poses):
+        self._check_edges(edges)
         P = _plain(poses)
         if P.requires_grad:
             return _VoLoss.apply(P, self.solver)
         return self.solver.vo_loss(P)
 
     def imu_loss(self, imu_drots=None, imu_dvels=None):
-        return self.solver.imu_loss()
+        """pvgo.py:95-111 on the tensors passed in (None: the measurements staged by the last forward / run_pvgo)."""
+        if imu_drots is None or imu_dvels is None:
+            return self.solver.imu_loss()
+        dr, dv = _plain(imu_drots), _plain(imu_dvels)
+        if dr.requires_grad or dv.requires_grad:
+            return _ImuLoss.apply(dr, dv, self.solver)
+        return self.solver.imu_loss(dr, dv)
 
     def align_to(self, target, idx=0):
         if idx != 0:
@@ -155,6 +223,8 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
     imu_rot_infos = np.ones(n_nodes - 1) * loss_weight[2] ** 2
     imu_vel_infos = np.ones(n_nodes - 1) * loss_weight[1] ** 2
     transvel_infos = np.ones(n_nodes - 1) * loss_weight[3] ** 2
+    if reproj is not None:
+        reproj_infos = np.ones(n_nodes - 1) * (loss_weight[4] / reproj.N) ** 2        # pvgo.py:130-131
 
     graph = PoseVelGraph(init_nodes, init_vels, reproj, links=links, device=device)
     # one host -> device transfer of the VO motions serves both the optimisation (detached, pvgo.py:146) and the outer
@@ -166,8 +236,10 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
     s.lm_reset(radius=float(radius), lm_min=1e-4, max_steps=int(max_steps), patience=int(patience),
                decreasing=float(decreasing), use_scheduler=1 if use_scheduler else 0)
     st = s.lm_run()
-    if st.info:
+    if st.info == 1:
         print('Linear solver failed. Breaking optimization step...')            # PyPose's message (A.4)
+    elif st.info:
+        raise IslamError(f'the device-side LM loop reported info={st.info} (see include/islam_pvgo.h)')
 
     if target == 'vo':                                                          # pvgo.py:186-189
         trans_loss, rot_loss = graph.vo_loss(links, vo_dev)
@@ -187,5 +259,7 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
     vels = vels_h
     covs = {'vo_rot': vo_rot_infos, 'imu_rot': imu_rot_infos, 'vo_trans': vo_trans_infos,
             'imu_vel': imu_vel_infos, 'transvel': transvel_infos}               # pvgo.py:199-203
+    if reproj is not None:
+        covs['reproj'] = reproj_infos
     run_pvgo.last_state = st
     return trans_loss, rot_loss, nodes, vels, covs

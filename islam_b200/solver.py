@@ -71,9 +71,10 @@ class PVGOSolver:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     # ------------------------------------------------------------------------------------------------ problem
-    def set_problem(self, vo_motions, imu_drots, imu_dtrans, imu_dvels, dts, loss_weight=(1, 1, 1, 1)):
+    def set_problem(self, vo_motions, imu_drots, imu_dtrans, imu_dvels, dts, loss_weight=(1, 1, 1, 1), reproj=None):
         """pvgo.py:125-165: information scalars are loss_weight**2 (VO trans and rot both use loss_weight[0])."""
         dev = self.device
+        self._set_reproj(reproj, loss_weight)
         Z = _f32(vo_motions, dev, (self.E, 7))
         dr = _f32(imu_drots, dev, (self.M, 4))
         dp = _f32(imu_dtrans, dev, (self.M, 3))
@@ -88,6 +89,10 @@ class PVGOSolver:
                                                  self._s()), 'islam_pvgo_set_problem')
         for t in (Z, dr, dp, dv, dt):                 # the D2D copies are in flight on our stream: keep the sources alive
             t.record_stream(self.stream)
+
+    def _set_reproj(self, reproj, loss_weight):
+        if reproj is not None:
+            raise NotImplementedError('the optional reprojection factor (pvgo.py:53-61) is not on the B200 path yet')
 
     def set_state(self, nodes, vels):
         n = _f32(nodes, self.device, (self.N, 7))
@@ -185,12 +190,21 @@ class PVGOSolver:
         P.record_stream(self.stream)
         return (tl, rl, gt, gr) if with_grad else (tl, rl)
 
-    def imu_loss(self):
+    def imu_loss(self, imu_drots=None, imu_dvels=None, with_grad=False):
+        """pvgo.py:95-111 for the given measurements (None: the ones staged by set_problem)."""
+        dr = _f32(imu_drots, self.device, (self.M, 4)) if imu_drots is not None else None
+        dv = _f32(imu_dvels, self.device, (self.M, 3)) if imu_dvels is not None else None
         tl, rl = self._new(self.M), self._new(self.M)
+        gr = self._new(self.M, 3) if with_grad else None
+        gv = self._new(self.M, 3) if with_grad else None
         self._enter()
-        _lib.check(self.L.islam_pvgo_imu_loss(self._h, _ptr(tl), _ptr(rl), self._s()), 'islam_pvgo_imu_loss')
+        _lib.check(self.L.islam_pvgo_imu_loss(self._h, _ptr(dr), _ptr(dv), _ptr(tl), _ptr(rl), _ptr(gr), _ptr(gv),
+                                              self._s()), 'islam_pvgo_imu_loss')
         self._exit()
-        return tl, rl
+        for t in (dr, dv):
+            if t is not None:
+                t.record_stream(self.stream)
+        return (tl, rl, gr, gv) if with_grad else (tl, rl)
 
     def align(self, target):
         t = _f32(target, self.device, (7,))

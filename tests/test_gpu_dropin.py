@@ -111,3 +111,44 @@ def test_reference_style_caller_on_the_shim():
     assert po.rel_pose_error(nodes.detach().cpu().numpy(), rn)['rel'] <= 1e-5
     assert np.abs(vels.detach().cpu().numpy() - rv).max() < 1e-4
     (tl.sum() + rl.sum()).backward()
+
+
+def test_failed_cholesky_surfaces_as_info_1(capsys):
+    """PyPose's "Linear solver failed. Breaking optimization step..." path: the parameters stay untouched,
+    the step is abandoned, and the failure is visible to the caller (LM state info = 1), never silent."""
+    from islam_b200.solver import PVGOSolver
+    g = synth.window()
+    s = PVGOSolver(g.N, g.links, device='cuda:0')
+    s.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
+    s.set_state(g.init_nodes, g.init_vels)
+    s.lm_reset(radius=g.radius, lm_max=-1.0, max_steps=3, use_scheduler=0)      # every pivot diagonal clamped to -1: not SPD
+    st = s.lm_run()
+    assert st.info == 1 and st.steps_done == 3
+    n, v = s.get_state()
+    assert np.array_equal(n.cpu().numpy(), g.init_nodes) and np.array_equal(v.cpu().numpy(), g.init_vels)
+    # through run_pvgo: a NaN measurement poisons J^T W J; the call returns (PyPose prints and breaks the step), info = 1
+    bad = _t(g.vo_motions).clone()
+    bad[3, 0] = float('nan')
+    tl, rl, nodes, vels, _ = run_pvgo(_t(g.init_nodes), _t(g.init_vels), bad, _t(g.links), _t(g.dts), _t(g.imu_drots),
+                                      _t(g.imu_dtrans), _t(g.imu_dvels), loss_weight=g.loss_weight)
+    assert run_pvgo.last_state.info == 1
+    assert 'Linear solver failed' in capsys.readouterr().out
+
+
+def test_two_live_graphs_do_not_share_device_state():
+    """Two PoseVelGraph objects over the same (N, links) — consecutive sliding windows — own separate solver handles."""
+    from islam_b200.pvgo import PoseVelGraph
+    g = synth.window()
+    a = PoseVelGraph(_t(g.init_nodes), _t(g.init_vels), links=_t(g.links))
+    shifted = g.init_nodes.copy()
+    shifted[:, 0] += 5.0
+    b = PoseVelGraph(_t(shifted), _t(g.init_vels), links=_t(g.links))
+    assert a.solver is not b.solver
+    assert np.array_equal(a.nodes.cpu().numpy(), g.init_nodes) and np.array_equal(b.nodes.cpu().numpy(), shifted)
+    # forward() stages the measurements of THIS call: new dts / motions are not ignored
+    args = (_t(g.links), _t(g.vo_motions), _t(g.imu_drots), _t(g.imu_dtrans), _t(g.imu_dvels), _t(g.dts))
+    r1 = a(*args)
+    r2 = a(args[0], args[1], args[2], args[3] + 0.25, args[4], args[5])
+    assert np.allclose((r1[3] - r2[3]).cpu().numpy(), 0.25, atol=1e-6)
+    with pytest.raises(Exception):
+        a.vo_loss(_t(g.links)[:-1], _t(g.vo_motions)[:-1])

@@ -77,3 +77,29 @@ def test_bias_subtraction_matches_reference_flags():
     rp, rr, _, rv = imu_oracle.integrate(imu['accels'] - ab, imu['gyros'] - gb, imu['dts'], imu['rgb2imu_sync'], 0, 19,
                                          imu['init'], imu['gravity'], True, np.float64)
     assert np.abs(p.numpy() - rp).max() < 1e-5 and np.abs(v.numpy() - rv).max() < 1e-5
+
+
+@pytest.mark.parametrize('F', [1, 10, 37])
+def test_pp_module_imupreintegrator_forward_every_k(F):
+    """pp.module.IMUPreintegrator.forward as /root/reference/imu_integrator.py:55-56,146 calls it: the state
+    after EVERY sample k = 1..F (offsets = arange), with an explicit init_state and with the constructor's state."""
+    import islam_b200.pypose_compat as pp
+    rng = np.random.default_rng(F)
+    dt = (0.01 + 0.002 * rng.random((F, 1))).astype(np.float32)
+    gyro = (0.3 * rng.normal(size=(F, 3))).astype(np.float32)
+    acc = (np.array([0.2, -0.1, 9.8]) + 0.5 * rng.normal(size=(F, 3))).astype(np.float32)
+    pos, vel = np.array([1.0, -2.0, 0.5], np.float32), np.array([0.7, 0.1, -0.2], np.float32)
+    rot = lie.so3_exp(np.array([[0.3, -0.2, 0.9]]))[0].astype(np.float32)
+    t = lambda a: torch.as_tensor(a).cuda()
+    integ = pp.module.IMUPreintegrator(t(pos), pp.SO3(t(rot)), t(vel), gravity=9.81007).to('cuda:0')
+    want = imu_oracle.preintegrate(dt.astype(np.float64), gyro.astype(np.float64), acc.astype(np.float64),
+                                   pos.astype(np.float64), rot.astype(np.float64), vel.astype(np.float64), 9.81007)
+    for init_state in ({'pos': t(pos), 'rot': pp.SO3(t(rot)), 'vel': t(vel)}, None):
+        out = integ(dt=t(dt), gyro=t(gyro), acc=t(acc), init_state=init_state)
+        assert out['pos'].shape == (1, F, 3) and out['rot'].shape == (1, F, 4) and out['vel'].shape == (1, F, 3)
+        assert isinstance(out['rot'], pp.LieTensor) and out['rot'].ltype is pp.SO3_type and out['pos'].is_cuda
+        assert np.abs(out['pos'][0].cpu().numpy() - want['pos']).max() < 1e-5 * max(1.0, np.abs(want['pos']).max())
+        assert np.abs(out['vel'][0].cpu().numpy() - want['vel']).max() < 1e-5 * max(1.0, np.abs(want['vel']).max())
+        assert _quat_close(out['rot'][0].cpu().numpy(), want['rot'], 1e-5)
+        # the last sample is what IMUModule.integrate keeps (imu_integrator.py:148-153)
+        assert out['pos'][..., -1, :].squeeze().shape == (3,)
