@@ -31,14 +31,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, phase_clocks=False):
-    """phase_clocks: developer build (lib/libislam_dbg.so) whose factor kernel stamps clock64() per phase (tools/phase_clocks.py)."""
-    out = LIB.replace('libislam_pvgo.so', 'libislam_dbg.so') if phase_clocks else LIB
+def build(force=False, verbose=False, phase_clocks=False, defines=(), name=None):
+    """phase_clocks: developer build (lib/libislam_dbg.so) whose factor kernel stamps clock64() per phase (tools/phase_clocks.py).
+    defines / name: further developer builds (extra -D flags, written to lib/<name>)."""
+    out = LIB.replace('libislam_pvgo.so', name or 'libislam_dbg.so') if phase_clocks else LIB
     if not force and not phase_clocks and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [_nvcc(), '-O3', '-std=c++17', *ARCH, '-lineinfo', '-Xcompiler', '-fPIC', '-shared',
-           '-diag-suppress', '177', '-o', out] + (['-DISLAM_PHASE_CLOCKS'] if phase_clocks else []) + \
+           '-diag-suppress', '177', '-o', out] + (['-DISLAM_PHASE_CLOCKS'] if phase_clocks else []) + [f'-D{d}' for d in defines] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, '-Xptxas'); cmd.insert(2, '-v')
@@ -52,4 +53,7 @@ def build(force=False, verbose=False, phase_clocks=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, phase_clocks='--phase-clocks' in sys.argv))
+    if '--chain-only' in sys.argv:      # developer experiment: the pivot chain of front4.cuh alone (panel / Schur warps exit)
+        print(build(phase_clocks=True, defines=('ISLAM_CHAIN_ONLY',), name='libislam_dbg2.so'))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, phase_clocks='--phase-clocks' in sys.argv))

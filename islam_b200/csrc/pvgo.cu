@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -11,6 +12,7 @@
 #include "linearize.cuh"
 #include "lm.cuh"
 #include "solver3.cuh"
+#include "front4.cuh"
 #include "symbolic.h"
 #include "symbolic3.h"
 
@@ -207,6 +209,7 @@ struct islam_pvgo {
     // per level: kernel variant (solver3.cuh MODE | VAR_SMALL_CTA: 256-thread CTAs, two per SM),
     // dynamic shared memory of the factor / back-substitution kernels
     std::vector<int> level_variant, level_smem_bytes, level_bs_bytes, level_count;
+    std::vector<int> level_front4;          // 1: the level runs the pipelined front kernel (front4.cuh)
     int n_sm = 148;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
     std::vector<int> level_nlocal, level_nshared;
@@ -252,6 +255,9 @@ extern "C" void islam_lm_default_params(islam_lm_params* p) {
 
 // kernel variant of one level (islam_pvgo::level_variant): solver3.cuh MODE in bits 0-1 | VAR_SMALL_CTA
 enum { VAR_SMALL_CTA = 4, VAR_TINY_CTA = 8 };
+
+// ISLAM_FRONT4=1 selects the pipelined front kernel (front4.cuh) where it applies; default: the barrier-stepped k_factor3
+static bool front4_enabled() { const char* e = std::getenv("ISLAM_FRONT4"); return e && e[0] == '1'; }
 
 template <int NT, int MINB, int MODE> static void set_factor_smem(int bytes) {
     cudaFuncSetAttribute(k_factor3<NT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -396,9 +402,11 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     if (max_optin <= 0) max_optin = 227 * 1024;
     set_factor_smem<512, 1, 2>(max_optin); set_factor_smem<512, 1, 1>(max_optin); set_factor_smem<512, 1, 0>(max_optin);
     set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin); set_factor_smem<128, 4, 1>(max_optin);
+    cudaFuncSetAttribute(k_front4<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     const int bs_optin = max_optin - 64;       // the back-substitution kernel also has a few bytes of static shared memory (its mbarrier)
     cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_optin);
     h->level_variant.assign(q.n_levels, 0);
+    h->level_front4.assign(q.n_levels, 0);
     h->level_count.assign(q.n_levels, 0);
     h->n_sm = n_sm;
     h->level_smem_bytes.assign(q.n_levels, 0);
@@ -406,11 +414,12 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     {
         std::vector<long long> need[3], bs_min(q.n_levels, 0), bs_full(q.n_levels, 0);
         for (auto& v : need) v.assign(q.n_levels, 0);
-        std::vector<int> count(q.n_levels, 0);
+        std::vector<int> count(q.n_levels, 0), pivcols(q.n_levels, 0);
         for (int f = 0; f < q.F; ++f) {
             if (f == q.dense_root) continue;
             const int l = q.f_level[f];
             const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub;
+            pivcols[l] = std::max(pivcols[l], Cf);
             for (int mode = 0; mode < 3; ++mode) need[mode][l] = std::max(need[mode][l], 8 * f3_smem_doubles(Rf, Cf, ub, mode));
             bs_min[l] = std::max(bs_min[l], 8 * bs3_smem_doubles(Rf, Cf, false));
             bs_full[l] = std::max(bs_full[l], 8 * bs3_smem_doubles(Rf, Cf, true));
@@ -420,9 +429,13 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             if (bs_min[l] > bs_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
             int var = need[2][l] <= max_optin ? 2 : (need[1][l] <= max_optin ? 1 : 0);
             long long bytes = need[var][l];
+            // whole frontal matrix in shared memory: the pipelined kernel, one 512-thread CTA per SM at every level width
+            // (multi-GPU: the shared fronts' stages 1 / 2 stay on k_factor3, same shared-memory layout)
+            if (var == 2 && front4_enabled() && pivcols[l] <= 9 * F4_MAX_STEPS) h->level_front4[l] = 1;
             // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency);
             // a leaf level wider than that: 128-thread CTAs, four per SM, update matrix written straight to global memory
-            if (l == 0 && count[l] > 2 * n_sm && 4 * (need[1][l] + 1024) <= smem_sm) { var = 1 | VAR_TINY_CTA; bytes = need[1][l]; }
+            if (h->level_front4[l]) { }
+            else if (l == 0 && count[l] > 2 * n_sm && 4 * (need[1][l] + 1024) <= smem_sm) { var = 1 | VAR_TINY_CTA; bytes = need[1][l]; }
             else if (var > 0 && count[l] > n_sm && 2 * (bytes + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
             h->level_variant[l] = var;
             h->level_count[l] = count[l];
@@ -610,6 +623,10 @@ static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int
     const islam_lm_params& q = h->prm;
     const size_t smem = (size_t)h->level_smem_bytes[l];
     const int var = h->level_variant[l];
+    if (stage == 0 && h->level_front4[l])
+        return launch_pdl(k_front4<512>, n, 512, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), h->fm,
+                          (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p,
+                          q.lm_min, q.lm_max, forced_scale, pre_ok, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p);
 #define F3_LAUNCH(NT, MINB, US)                                                                                          \
     launch_pdl(k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
                h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \

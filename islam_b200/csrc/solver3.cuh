@@ -25,6 +25,8 @@ namespace islam {
 __device__ long long g_phase_clk[64];
 __device__ int g_phase_grid = 1;
 #define PHASE(n) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
+// same, stamped by an arbitrary thread (front4.cuh: first thread of the panel / Schur warps)
+#define PHASE_BY(n, who) do { if (blockIdx.x == gridDim.x / 2 && (who) && gridDim.x == g_phase_grid) g_phase_clk[n] = clock64(); } while (0)
 // per front: globaltimer at CTA start, after the grid dependency, at the end; SM id  (tools/level_timeline.py)
 __device__ unsigned long long g_front_t[4][8192];
 __device__ unsigned long long g_bs_t[4][8192];
@@ -32,9 +34,13 @@ __device__ unsigned long long g_bs_t[4][8192];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define FRONT_T(k, f) do { if (threadIdx.x == 0 && (f) < 8192) g_front_t[k][f] = (k) == 3 ? (unsigned long long)smid() : gtime(); } while (0)
+// end of a front whose warps finish at different times (front4.cuh): the latest stamp wins
+#define FRONT_END(f) do { if ((threadIdx.x & 31) == 0 && (f) < 8192) atomicMax(&g_front_t[2][f], gtime()); } while (0)
 #else
 #define PHASE(n) do { } while (0)
+#define PHASE_BY(n, who) do { } while (0)
 #define FRONT_T(k, f) do { } while (0)
+#define FRONT_END(f) do { } while (0)
 #define BS_T(k, f) do { } while (0)
 #endif
 

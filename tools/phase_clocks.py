@@ -3,7 +3,7 @@
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from islam_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), 'libislam_dbg.so')
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), os.environ.get('ISLAM_DBG_LIB', 'libislam_dbg.so'))
 import numpy as np, torch
 from islam_b200 import synth
 from islam_b200.solver import PVGOSolver
@@ -31,3 +31,11 @@ for grid in [int(a) for a in sys.argv[1:]] or [1]:
             print('  jb', jb, 'start', c[10 + 3 * jb] - t0, 'trsm', c[11 + 3 * jb] - t0, 'update', c[12 + 3 * jb] - t0)
     for k in (4, 5, 6):
         print(' ', names[k], c[k] - t0)
+    if c[30] > t0:          # front4: panel / Schur warps
+        for jb in range(7):
+            if c[30 + 3 * jb] > t0:
+                print('  panel jb', jb, 'chain flag seen', c[30 + 3 * jb] - t0, 'row solve done', c[31 + 3 * jb] - t0, 'trailing + store done', c[32 + 3 * jb] - t0)
+        for jb in range(6):
+            if c[48 + 2 * jb] > t0:
+                print('  schur jb', jb, 'panel flag seen', c[48 + 2 * jb] - t0, 'rank-9 done', c[49 + 2 * jb] - t0)
+        print('  schur applied', c[60] - t0, 'panel warps done', c[61] - t0)

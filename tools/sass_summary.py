@@ -48,7 +48,7 @@ def main():
     print(f'# {os.path.relpath(LIB, ROOT)}  cubin architectures: {sorted(arch)}')
     print('# kernel | total instructions | ' + ' '.join(KEYS))
     for n, c in counts.items():
-        short = demangle.get(n, n).replace('islam::', '').replace('(anonymous namespace)::', '').replace('<unnamed>::', '')
+        short = demangle.get(n, n).replace('islam::', '').replace('(anonymous namespace)::', '').replace('<unnamed>::', '').replace('(int)', '').replace('(bool)', '')
         short = short.split('(')[0].replace('void ', '')
         print(f'{short:60s} {c["_total"]:7d}  ' + ' '.join(f'{k}={c[k]}' for k in KEYS if c[k]))
 
