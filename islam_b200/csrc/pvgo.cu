@@ -402,7 +402,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     if (max_optin <= 0) max_optin = 227 * 1024;
     set_factor_smem<512, 1, 2>(max_optin); set_factor_smem<512, 1, 1>(max_optin); set_factor_smem<512, 1, 0>(max_optin);
     set_factor_smem<256, 2, 2>(max_optin); set_factor_smem<256, 2, 1>(max_optin); set_factor_smem<128, 4, 1>(max_optin);
-    cudaFuncSetAttribute(k_front4<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    cudaFuncSetAttribute(k_front4<F4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     const int bs_optin = max_optin - 64;       // the back-substitution kernel also has a few bytes of static shared memory (its mbarrier)
     cudaFuncSetAttribute(k_backsolve3, cudaFuncAttributeMaxDynamicSharedMemorySize, bs_optin);
     h->level_variant.assign(q.n_levels, 0);
@@ -414,12 +414,19 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     {
         std::vector<long long> need[3], bs_min(q.n_levels, 0), bs_full(q.n_levels, 0);
         for (auto& v : need) v.assign(q.n_levels, 0);
-        std::vector<int> count(q.n_levels, 0), pivcols(q.n_levels, 0);
+        std::vector<int> count(q.n_levels, 0), pivcols(q.n_levels, 0), maxub(q.n_levels, 0);
+        std::vector<long long> stage(q.n_levels, 0);      // front4: shared-memory staging of a front's two children (TMA)
         for (int f = 0; f < q.F; ++f) {
             if (f == q.dense_root) continue;
             const int l = q.f_level[f];
             const int Cf = 3 * q.f_npad[f], ub = 3 * q.f_nb[f] + 1, Rf = Cf + ub;
             pivcols[l] = std::max(pivcols[l], Cf);
+            {
+                long long both = 0;
+                for (int k = q.f_child_off[f]; k < q.f_child_off[f + 1]; ++k) both += f3_ulen(3 * q.f_nb[q.f_children[k]] + 1);
+                if (q.f_child_off[f + 1] - q.f_child_off[f] == 2) stage[l] = std::max(stage[l], 8 * (f3_smem_doubles(Rf, Cf, ub, 2) + both));
+            }
+            maxub[l] = std::max(maxub[l], ub);
             for (int mode = 0; mode < 3; ++mode) need[mode][l] = std::max(need[mode][l], 8 * f3_smem_doubles(Rf, Cf, ub, mode));
             bs_min[l] = std::max(bs_min[l], 8 * bs3_smem_doubles(Rf, Cf, false));
             bs_full[l] = std::max(bs_full[l], 8 * bs3_smem_doubles(Rf, Cf, true));
@@ -429,12 +436,12 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
             if (bs_min[l] > bs_optin) { delete h; return -5; }    // boundary too wide for the back-substitution kernel
             int var = need[2][l] <= max_optin ? 2 : (need[1][l] <= max_optin ? 1 : 0);
             long long bytes = need[var][l];
-            // whole frontal matrix in shared memory: the pipelined kernel, one 512-thread CTA per SM at every level width
+            // whole frontal matrix in shared memory and a shape the pipelined kernel's register tiles cover: one 320-thread CTA per SM
             // (multi-GPU: the shared fronts' stages 1 / 2 stay on k_factor3, same shared-memory layout)
-            if (var == 2 && front4_enabled() && pivcols[l] <= 9 * F4_MAX_STEPS) h->level_front4[l] = 1;
+            if (var == 2 && front4_enabled() && pivcols[l] <= 9 * F4_MAX_STEPS && maxub[l] <= F4_MAX_NBR) h->level_front4[l] = 1;
             // more fronts than SMs: 256-thread CTAs, two per SM (throughput); otherwise one 512-thread CTA per SM (latency);
             // a leaf level wider than that: 128-thread CTAs, four per SM, update matrix written straight to global memory
-            if (h->level_front4[l]) { }
+            if (h->level_front4[l]) { if (stage[l] > bytes && stage[l] <= max_optin) bytes = stage[l]; }
             else if (l == 0 && count[l] > 2 * n_sm && 4 * (need[1][l] + 1024) <= smem_sm) { var = 1 | VAR_TINY_CTA; bytes = need[1][l]; }
             else if (var > 0 && count[l] > n_sm && 2 * (bytes + 1024) <= smem_sm) var |= VAR_SMALL_CTA;
             h->level_variant[l] = var;
@@ -624,9 +631,10 @@ static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int
     const size_t smem = (size_t)h->level_smem_bytes[l];
     const int var = h->level_variant[l];
     if (stage == 0 && h->level_front4[l])
-        return launch_pdl(k_front4<512>, n, 512, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), h->fm,
+        return launch_pdl(k_front4<F4_NT>, n, F4_NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), h->fm,
                           (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p,
-                          q.lm_min, q.lm_max, forced_scale, pre_ok, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p);
+                          q.lm_min, q.lm_max, forced_scale, pre_ok, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p,
+                          (int)(smem / sizeof(double)));
 #define F3_LAUNCH(NT, MINB, US)                                                                                          \
     launch_pdl(k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
                h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \

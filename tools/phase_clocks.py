@@ -31,6 +31,7 @@ for grid in [int(a) for a in sys.argv[1:]] or [1]:
             print('  jb', jb, 'start', c[10 + 3 * jb] - t0, 'trsm', c[11 + 3 * jb] - t0, 'update', c[12 + 3 * jb] - t0)
     for k in (4, 5, 6):
         print(' ', names[k], c[k] - t0)
+    print('  front4 jb 2 detail: loads done', c[8] - t0, 'diag done', c[9] - t0, 'global stores issued', c[5] - t0, 'look-ahead init loaded', c[6] - t0, 'look-ahead fma done', c[7] - t0)
     if c[30] > t0:          # front4: panel / Schur warps
         for jb in range(7):
             if c[30 + 3 * jb] > t0:
