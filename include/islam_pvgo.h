@@ -100,6 +100,14 @@ int islam_pvgo_set_problem(islam_pvgo* h, const float* vo_motions /* E x 7 */, c
                            const float* imu_dtrans /* M x 3 */, const float* imu_dvels /* M x 3 */,
                            const float* dts /* M */, const double info_w[4] /* host: w0^2,w1^2,w2^2,w3^2 */,
                            void* stream);
+/* optional 5th residual group, the sparse reprojection factor (pvgo.py:53-61,130-165 with dense_ba.py:276-305
+ * SparseReprojectionLoss): per consecutive pair i, n_points camera-frame points of pose i (point3d, M x n_points x 3) and
+ * their target pixels in the camera at pose i+1 (M x n_points x 2), both device pointers (copied); intrinsics fx, fy, cx, cy
+ * and the rgb2imu pose (7) are host arrays; info_w = (loss_weight[4] / n_points)^2.  motion[0] is the constant 0.1 as at
+ * pvgo.py:57 (zero Jacobian for pair 0).  n_points = 0 removes the factor.  Single GPU only (-6 with n_parts > 1). */
+int islam_pvgo_set_reproj(islam_pvgo* h, const float* point3d, const float* target, int32_t n_points,
+                          const float intrinsics[4], const float rgb2imu[7], double info_w, void* stream);
+int islam_pvgo_get_reproj_residuals(islam_pvgo* h, float* reprojerr /* M x 2 n_points */, void* stream);
 int islam_pvgo_set_state(islam_pvgo* h, const float* nodes /* N x 7 */, const float* vels /* N x 3 */, void* stream);
 int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, void* stream);
 

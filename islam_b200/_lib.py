@@ -54,6 +54,8 @@ _SIGS = {
     'islam_lm_default_params': (None, [C.POINTER(LMParams)]),
     'islam_pvgo_set_problem': (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(C.c_double * 4), _P]),
     'islam_pvgo_set_state': (C.c_int, [_P, _P, _P, _P]),
+    'islam_pvgo_set_reproj': (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_float * 4), C.POINTER(C.c_float * 7), C.c_double, _P]),
+    'islam_pvgo_get_reproj_residuals': (C.c_int, [_P, _P, _P]),
     'islam_pvgo_get_state': (C.c_int, [_P, _P, _P, _P]),
     'islam_pvgo_linearize': (C.c_int, [_P, _P]),
     'islam_pvgo_get_residuals': (C.c_int, [_P, _P, _P, _P, _P, _P]),

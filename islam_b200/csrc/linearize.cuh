@@ -25,7 +25,12 @@ struct ProblemView {
     const int* edge_owner;  // [E] window that owns the factor (multi-GPU) or nullptr
     const int* pair_owner;  // [M]
     int part;
-    const double* w;        // [4] information scalars w0..w3 in device memory (pvgo.py:125-129)
+    const double* w;        // [5] information scalars w0..w3 (pvgo.py:125-129) and the reprojection one (pvgo.py:131) in device memory
+    // optional sparse reprojection factor (pvgo.py:53-61, dense_ba.py:276-305); rp_n = 0: absent
+    const float* rp_pts;    // [M, rp_n, 3] camera-frame points of pose i
+    const float* rp_tgt;    // [M, rp_n, 2] target pixels in the camera at pose i+1
+    const float* rp_cal;    // [11] fx, fy, cx, cy, rgb2imu pose (7)
+    int rp_n;
 };
 
 struct LinBuffers {
@@ -35,7 +40,10 @@ struct LinBuffers {
     double* q_vo;    // [E,6]  w0 * J^T r
     float* r_imu;    // [M,9]  adjvelerr(3), imuroterr(3), transvelerr(3)
     float* J_rot;    // [M,9]  Jl^-1(r) dR^T Ri^T
-    double* loss_part;   // [nblk_vo + nblk_imu] partial sums of r^2 (unweighted — PyPose model.loss)
+    double* loss_part;   // [nblk_vo + nblk_imu + nblk_rp] partial sums of r^2 (unweighted — PyPose model.loss)
+    float* r_rp;     // [M, 2 rp_n] reprojection residuals
+    double* S_rp;    // [M,36] UNWEIGHTED sum over the pair's points of J^T J (J = d r / d delta_i; d r / d delta_{i+1} = -J)
+    double* q_rp;    // [M,6]  unweighted J^T r
 };
 
 __device__ __forceinline__ void load7(const float* p, float* x) {
@@ -244,16 +252,167 @@ imu_block(int blk, const LMState* __restrict__ st, const float* __restrict__ nod
     }
 }
 
-// one launch for both factor families: blocks [0, nblk_vo) take VO / loop-closure edges, the rest the IMU pairs
+// ---------------------------------------------------------------------------------------------- reprojection factors
+// One warp per consecutive pair i (pvgo.py:53-61 with dense_ba.py:299-305): motion = X_i^-1 X_{i+1} (motion_0 overwritten by
+// the constant 0.1, all seven numbers: pvgo.py:57), T = C^-1 motion C, r = point2pixel(P, K, T^-1) - target for the pair's
+// points.  Every op on that path is a LieTensor op, so PyPose's Jacobian is the true left-tangent one:
+// d r / d delta_i = Pi(p') R_C^T R_j^T [I | -[W]x], W = X_i C P, d r / d delta_{i+1} = -(that); pair 0 is a constant (zero J).
+// mode 0 writes r, the unweighted per-pair J^T J / J^T r (float64 sums over the points, fixed order) and the loss partials;
+// mode 1 evaluates the trial residuals and the (J D)^T (2 r + J D) term from the stored per-pair sums.
+constexpr int RP_PAIRS = LIN_THREADS / 32;
+template <int MODE>
+__device__ __forceinline__ void
+rp_block(int blk, const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
+         ProblemView pv, LinBuffers lb, const double* __restrict__ D, double* __restrict__ part_out, int force) {
+    if (!force) {
+        if (!st->active) return;
+        if (MODE == 0 && !st->do_lin) return;
+    }
+    const int cur = st->cur;
+    const float* nodes = (MODE == 0) ? (cur ? nodes1 : nodes0) : (cur ? nodes0 : nodes1);
+    __shared__ double shl[RP_PAIRS], shq[RP_PAIRS];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int i = blk * RP_PAIRS + wp;
+    const bool mine = i < pv.M && (pv.pair_owner == nullptr || pv.pair_owner[i] == pv.part);
+    double lsum = 0.0, qsum = 0.0;
+    if (mine) {
+        const int np_ = pv.rp_n;
+        const float fx = pv.rp_cal[0], fy = pv.rp_cal[1], cx = pv.rp_cal[2], cy = pv.rp_cal[3];
+        float C[7], Xi[7], Xj[7], Ci[7], mo[7], T1[7], T[7], Ti[7];
+        load7(pv.rp_cal + 4, C);
+        load7(nodes + 7 * (size_t)i, Xi);
+        load7(nodes + 7 * (size_t)(i + 1), Xj);
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) mo[k] = 0.1f;                    // pvgo.py:57
+        } else {
+            float Xii[7];
+            se3_inv(Xi, Xii);
+            se3_mul(Xii, Xj, mo);                                        // pvgo.py:54-56
+        }
+        se3_inv(C, Ci);
+        se3_mul(Ci, mo, T1);
+        se3_mul(T1, C, T);                                               // dense_ba.py:300
+        se3_inv(T, Ti);
+        float A[9];                                                       // R_C^T R_j^T
+        if (MODE == 0) {
+            float RC[9], Rj[9];
+            q_matrix(C + 3, RC);
+            q_matrix(Xj + 3, Rj);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v += RC[3 * k + a] * Rj[3 * b + k];
+                    A[3 * a + b] = v;
+                }
+        }
+        double S[21], q[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) S[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] = 0.0;
+        const float* pts = pv.rp_pts + 3 * (size_t)i * np_;
+        const float* tgt = pv.rp_tgt + 2 * (size_t)i * np_;
+        for (int p = lane; p < np_; p += 32) {
+            const float P[3] = {pts[3 * p], pts[3 * p + 1], pts[3 * p + 2]};
+            float pc[3];
+            q_rot(Ti + 3, P, pc);
+            pc[0] += Ti[0]; pc[1] += Ti[1]; pc[2] += Ti[2];
+            const float z = copysignf(fmaxf(fabsf(pc[2]), 1.17549435e-38f), pc[2] >= 0.f ? 1.f : -1.f);   // homo2cart's clamp
+            const float r0 = fx * pc[0] / z + cx - tgt[2 * p], r1 = fy * pc[1] / z + cy - tgt[2 * p + 1];
+            lsum += (double)r0 * r0 + (double)r1 * r1;
+            if (MODE == 0) {
+                lb.r_rp[2 * ((size_t)i * np_ + p)] = r0;
+                lb.r_rp[2 * ((size_t)i * np_ + p) + 1] = r1;
+                if (i > 0) {
+                    float B[3], W[3];
+                    q_rot(C + 3, P, B);
+                    B[0] += C[0]; B[1] += C[1]; B[2] += C[2];
+                    q_rot(Xi + 3, B, W);
+                    W[0] += Xi[0]; W[1] += Xi[1]; W[2] += Xi[2];
+                    // rows of Pi A (2 x 3), then J = (Pi A) [I | -[W]x]
+                    const float iz = 1.f / z;
+                    const float p0[3] = {fx * iz, 0.f, -fx * pc[0] * iz * iz}, p1[3] = {0.f, fy * iz, -fy * pc[1] * iz * iz};
+                    float M0[3], M1[3];
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        M0[b] = p0[0] * A[b] + p0[1] * A[3 + b] + p0[2] * A[6 + b];
+                        M1[b] = p1[0] * A[b] + p1[1] * A[3 + b] + p1[2] * A[6 + b];
+                    }
+                    // row vector m times -[W]x = (m2 W1 - m1 W2, m0 W2 - m2 W0, m1 W0 - m0 W1)
+                    double J0[6] = {M0[0], M0[1], M0[2], (double)M0[2] * W[1] - (double)M0[1] * W[2],
+                                    (double)M0[0] * W[2] - (double)M0[2] * W[0], (double)M0[1] * W[0] - (double)M0[0] * W[1]};
+                    double J1[6] = {M1[0], M1[1], M1[2], (double)M1[2] * W[1] - (double)M1[1] * W[2],
+                                    (double)M1[0] * W[2] - (double)M1[2] * W[0], (double)M1[1] * W[0] - (double)M1[0] * W[1]};
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        q[a] += J0[a] * r0 + J1[a] * r1;
+#pragma unroll
+                        for (int b = a; b < 6; ++b) S[k++] += J0[a] * J0[b] + J1[a] * J1[b];
+                    }
+                }
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int k = 0; k < 21; ++k) S[k] = warp_sum(S[k]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) q[k] = warp_sum(q[k]);
+            if (lane == 0) {
+                double* So = lb.S_rp + 36 * (size_t)i;
+                int k = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a; b < 6; ++b) { So[6 * a + b] = S[k]; So[6 * b + a] = S[k]; ++k; }
+#pragma unroll
+                for (int a = 0; a < 6; ++a) lb.q_rp[6 * (size_t)i + a] = q[a];
+            }
+        } else if (lane == 0) {
+            // (J D)^T (2 r + J D) summed over the pair's rows = 2 d^T (J^T r) + d^T (J^T J) d, d = D_i - D_{i+1}
+            const double* So = lb.S_rp + 36 * (size_t)i;
+            const double* qo = lb.q_rp + 6 * (size_t)i;
+            double d[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) d[a] = D[9 * (size_t)i + a] - D[9 * (size_t)(i + 1) + a];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double sd = 0.0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) sd += So[6 * a + b] * d[b];
+                qsum += d[a] * (2.0 * qo[a] + sd);
+            }
+        }
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) { shl[wp] = lsum; shq[wp] = qsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double l = 0.0, qq = 0.0;
+#pragma unroll
+        for (int k = 0; k < RP_PAIRS; ++k) { l += shl[k]; qq += shq[k]; }
+        part_out[2 * blk] = l;
+        part_out[2 * blk + 1] = MODE == 1 ? qq : 0.0;
+    }
+}
+
+// one launch for all factor families: blocks [0, nblk_vo) take VO / loop-closure edges, the next nblk_imu the IMU pairs, the rest
+// (if the optional reprojection factor is present) four pairs' reprojection residuals each
 template <int MODE>
 __global__ void __launch_bounds__(LIN_THREADS)
 k_factors(const LMState* __restrict__ st, const float* __restrict__ nodes0, const float* __restrict__ nodes1,
           const float* __restrict__ vels0, const float* __restrict__ vels1, ProblemView pv, LinBuffers lb,
-          const double* __restrict__ D, double* __restrict__ part_out, int nblk_vo, int force) {
+          const double* __restrict__ D, double* __restrict__ part_out, int nblk_vo, int nblk_imu, int force) {
     cudaGridDependencySynchronize();           // PDL: only the launch latency overlaps the previous kernel
     cudaTriggerProgrammaticLaunchCompletion();
     if ((int)blockIdx.x < nblk_vo) vo_block<MODE>(blockIdx.x, st, nodes0, nodes1, pv, lb, D, part_out, force);
-    else imu_block<MODE>(blockIdx.x - nblk_vo, st, nodes0, nodes1, vels0, vels1, pv, lb, D, part_out + 2 * nblk_vo, force);
+    else if ((int)blockIdx.x < nblk_vo + nblk_imu)
+        imu_block<MODE>(blockIdx.x - nblk_vo, st, nodes0, nodes1, vels0, vels1, pv, lb, D, part_out + 2 * nblk_vo, force);
+    else rp_block<MODE>(blockIdx.x - nblk_vo - nblk_imu, st, nodes0, nodes1, pv, lb, D, part_out + 2 * (nblk_vo + nblk_imu), force);
 }
 
 // ---------------------------------------------------------------------------------------------- assembly
@@ -312,6 +471,10 @@ assemble_nodes_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
             if (a >= 6) v += (has_prev ? pv.w[1] : 0.0) + (has_next ? pv.w[1] + pv.w[3] * dtn * dtn : 0.0);
         }
         if (has_next && ((a < 3 && b == a + 6) || (b < 3 && a == b + 6))) v += pv.w[3] * dtn;   // tau_i - v_i cross
+        if (pv.rp_n > 0 && a < 6 && b < 6) {                                                     // reprojection: +-J on both ends
+            if (has_prev) v += pv.w[4] * lb.S_rp[36 * (size_t)(n - 1) + 6 * a + b];
+            if (has_next) v += pv.w[4] * lb.S_rp[36 * (size_t)n + 6 * a + b];
+        }
         Hd[81 * (size_t)n + idx] = v;
     }
     if (lane < 9) {
@@ -348,6 +511,10 @@ assemble_nodes_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
             int aa = a - 6;
             if (has_prev) v -= pv.w[1] * (double)rp[aa];
             if (has_next) v += pv.w[1] * (double)rn[aa] - pv.w[3] * dtn * (double)rn[6 + aa];
+        }
+        if (pv.rp_n > 0 && a < 6) {                     // J(delta_i) = +J of pair i, J(delta_{i+1}) = -J
+            if (has_prev) v -= pv.w[4] * lb.q_rp[6 * (size_t)(n - 1) + a];
+            if (has_next) v += pv.w[4] * lb.q_rp[6 * (size_t)n + a];
         }
         g[9 * (size_t)n + a] = v;
     }
@@ -388,6 +555,7 @@ assemble_pairs_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
                 if (a >= 6) v -= pv.w[1];
             }
             if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w[3] * dt;   // (v_lo, tau_hi)
+            if (pv.rp_n > 0 && a < 6 && b < 6) v -= pv.w[4] * lb.S_rp[36 * (size_t)lo + 6 * a + b];
         }
         Ho[81 * (size_t)p + idx] = v;
     }

@@ -205,7 +205,10 @@ struct islam_pvgo {
     DevBuf<islam_lm_params> d_prm;
     DevBuf<double> d_w;
     LMState* st_host = nullptr;     // pinned mirror
-    int nblk_vo = 0, nblk_imu = 0;
+    int nblk_vo = 0, nblk_imu = 0, nblk_rp = 0;      // nblk_rp > 0: the optional reprojection factor is staged
+    DevBuf<float> rp_pts, rp_tgt, rp_cal, r_rp;
+    DevBuf<double> S_rp, q_rp;
+    int n_blocks() const { return nblk_vo + nblk_imu + nblk_rp; }
     // per level: kernel variant (solver3.cuh MODE | VAR_SMALL_CTA: 256-thread CTAs, two per SM),
     // dynamic shared memory of the factor / back-substitution kernels
     std::vector<int> level_variant, level_smem_bytes, level_bs_bytes, level_count;
@@ -233,9 +236,10 @@ struct islam_pvgo {
                              &d_bs_count};
         for (auto* b : ib) b->release();
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
-                               &r_imu, &J_rot};
+                               &r_imu, &J_rot, &rp_pts, &rp_tgt, &rp_cal, &r_rp};
         for (auto* b : fb) b->release();
-        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x};
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x,
+                                &S_rp, &q_rp};
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_Ioff.release(); d_shared_off.release(); d_dmap.release();
         st.release(); d_prm.release(); d_w.release();
@@ -320,7 +324,10 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     AL(S_vo, 36 * (size_t)E); AL(q_vo, 6 * (size_t)E);
     h->nblk_vo = (E + LIN_THREADS - 1) / LIN_THREADS;
     h->nblk_imu = (p.M + LIN_THREADS - 1) / LIN_THREADS;
-    AL(lin_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu)); AL(trial_part, 2 * (size_t)(h->nblk_vo + h->nblk_imu));
+    {
+        const size_t nb_all = (size_t)h->nblk_vo + h->nblk_imu + (p.M + RP_PAIRS - 1) / RP_PAIRS;     // room for the optional reprojection blocks
+        AL(lin_part, 2 * nb_all); AL(trial_part, 2 * nb_all);
+    }
     AL(sums, 8);
     AL(Hd, 81 * (size_t)N); AL(Ho, 81 * (size_t)p.P); AL(g, 9 * (size_t)N); AL(D, 9 * (size_t)N);
     UP(d_node_eoff, p.node_eoff); UP(d_node_edges, p.node_edges); UP(d_pair_lo, p.pair_lo); UP(d_pair_hi, p.pair_hi);
@@ -388,7 +395,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
     }
     AL(Lbuf, (size_t)q.L_doubles); AL(Ubuf, (size_t)q.U_doubles); AL(Linv, (size_t)std::max(1LL, q.I_doubles));
-    AL(st, 1); AL(d_prm, 1); AL(d_w, 4);
+    AL(st, 1); AL(d_prm, 1); AL(d_w, 5);
     cudaMemset(h->D.p, 0, sizeof(double) * 9 * (size_t)N);
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
@@ -483,11 +490,12 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     pv.dvel = h->dvel.p; pv.dt = h->dt.p;
     pv.edge_owner = h->edge_owner.p; pv.pair_owner = h->pair_owner.p; pv.part = opts.part;
     pv.w = h->d_w.p;
-    { double ones[4] = {1, 1, 1, 1}; cudaMemcpy(h->d_w.p, ones, sizeof(ones), cudaMemcpyHostToDevice); }
+    { double ones[5] = {1, 1, 1, 1, 0}; cudaMemcpy(h->d_w.p, ones, sizeof(ones), cudaMemcpyHostToDevice); }
+    pv.rp_pts = nullptr; pv.rp_tgt = nullptr; pv.rp_cal = nullptr; pv.rp_n = 0;
     cudaMemcpy(h->d_prm.p, &h->prm, sizeof(h->prm), cudaMemcpyHostToDevice);
     LinBuffers& lb = h->lb;
     lb.r_vo = h->r_vo.p; lb.J_vo = h->J_vo.p; lb.S_vo = h->S_vo.p; lb.q_vo = h->q_vo.p; lb.r_imu = h->r_imu.p;
-    lb.J_rot = h->J_rot.p; lb.loss_part = h->lin_part.p;
+    lb.J_rot = h->J_rot.p; lb.loss_part = h->lin_part.p; lb.r_rp = nullptr; lb.S_rp = nullptr; lb.q_rp = nullptr;
     AsmView& av = h->av;
     av.node_eoff = h->d_node_eoff.p; av.node_edges = h->d_node_edges.p; av.pair_lo = h->d_pair_lo.p;
     av.pair_hi = h->d_pair_hi.p; av.pair_adj = h->d_pair_adj.p; av.pair_eoff = h->d_pair_eoff.p;
@@ -566,6 +574,44 @@ extern "C" int islam_pvgo_set_state(islam_pvgo* h, const float* nodes, const flo
     return (int)cudaGetLastError();
 }
 
+// optional 5th factor family (pvgo.py:53-61): n_points = 0 removes it
+extern "C" int islam_pvgo_set_reproj(islam_pvgo* h, const float* point3d, const float* target, int32_t n_points,
+                                     const float intrinsics[4], const float rgb2imu[7], double info_w, void* stream) {
+    if (!h || n_points < 0) return -1;
+    if (h->opts.n_parts > 1 && n_points > 0) return -6;            // single-GPU only
+    cudaStream_t s = (cudaStream_t)stream;
+    const Plan& p = h->plan;
+    const int was = h->nblk_rp;
+    if (n_points == 0) {
+        h->nblk_rp = 0; h->pv.rp_n = 0;
+    } else {
+        if (!point3d || !target || !intrinsics || !rgb2imu) return -1;
+        const size_t need_p = 3 * (size_t)p.M * n_points, need_t = 2 * (size_t)p.M * n_points;
+        if (h->rp_pts.n < need_p) { h->rp_pts.release(); CK(h->rp_pts.alloc(need_p)); }
+        if (h->rp_tgt.n < need_t) { h->rp_tgt.release(); CK(h->rp_tgt.alloc(need_t)); h->r_rp.release(); CK(h->r_rp.alloc(need_t)); }
+        if (!h->rp_cal.p) { CK(h->rp_cal.alloc(11)); CK(h->S_rp.alloc(36 * (size_t)p.M)); CK(h->q_rp.alloc(6 * (size_t)p.M)); }
+        CK(cudaMemcpyAsync(h->rp_pts.p, point3d, sizeof(float) * need_p, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(h->rp_tgt.p, target, sizeof(float) * need_t, cudaMemcpyDeviceToDevice, s));
+        float cal[11];
+        for (int k = 0; k < 4; ++k) cal[k] = intrinsics[k];
+        for (int k = 0; k < 7; ++k) cal[4 + k] = rgb2imu[k];
+        CK(cudaMemcpyAsync(h->rp_cal.p, cal, sizeof(cal), cudaMemcpyHostToDevice, s));      // pageable source: staged before return
+        CK(cudaMemcpyAsync(h->d_w.p + 4, &info_w, sizeof(double), cudaMemcpyHostToDevice, s));
+        h->pv.rp_pts = h->rp_pts.p; h->pv.rp_tgt = h->rp_tgt.p; h->pv.rp_cal = h->rp_cal.p; h->pv.rp_n = n_points;
+        h->lb.r_rp = h->r_rp.p; h->lb.S_rp = h->S_rp.p; h->lb.q_rp = h->q_rp.p;
+        h->nblk_rp = (p.M + RP_PAIRS - 1) / RP_PAIRS;
+    }
+    // the captured graph bakes grid sizes and the problem view in: re-capture when the factor set (or its size) changed
+    if ((was != h->nblk_rp || n_points > 0) && h->graph_try) { cudaGraphExecDestroy(h->graph_try); h->graph_try = nullptr; }
+    return 0;
+}
+
+extern "C" int islam_pvgo_get_reproj_residuals(islam_pvgo* h, float* out, void* stream) {
+    if (!h || !out || h->nblk_rp == 0) return -1;
+    CK(cudaMemcpyAsync(out, h->r_rp.p, sizeof(float) * 2 * (size_t)h->plan.M * h->pv.rp_n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 static int read_state(islam_pvgo* h, cudaStream_t s) {
     CK(cudaMemcpyAsync(h->st_host, h->st.p, sizeof(LMState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -598,9 +644,9 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 // assembly of the block-diagonal and off-diagonal 9x9 blocks
 static int launch_linearize(islam_pvgo* h, cudaStream_t s, int force) {
     const Plan& p = h->plan;
-    CK(launch_pdl(k_factors<0>, h->nblk_vo + h->nblk_imu, LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
+    CK(launch_pdl(k_factors<0>, h->n_blocks(), LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
                   (const float*)h->nodes[1].p, (const float*)h->vels[0].p, (const float*)h->vels[1].p, h->pv, h->lb,
-                  (const double*)h->D.p, h->lin_part.p, h->nblk_vo, force));
+                  (const double*)h->D.p, h->lin_part.p, h->nblk_vo, h->nblk_imu, force));
     const int nbn = (p.N * 32 + 127) / 128, nbp = (p.P * 32 + 127) / 128;
     CK(launch_pdl(k_assemble, nbn + nbp, 128, 0, s, (const LMState*)h->st.p, h->pv, h->lb, h->av, h->Hd.p, h->Ho.p, h->g.p, nbn, force));
     return (int)cudaGetLastError();
@@ -611,9 +657,9 @@ static int launch_trial(islam_pvgo* h, cudaStream_t s) {
     const Plan& p = h->plan;
     CK(launch_pdl(k_retract, (p.N + 127) / 128, 128, 0, s, (const LMState*)h->st.p, h->nodes[0].p, h->nodes[1].p, h->vels[0].p,
                   h->vels[1].p, (const double*)h->D.p, p.N));
-    CK(launch_pdl(k_factors<1>, h->nblk_vo + h->nblk_imu, LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
+    CK(launch_pdl(k_factors<1>, h->n_blocks(), LIN_THREADS, 0, s, (const LMState*)h->st.p, (const float*)h->nodes[0].p,
                   (const float*)h->nodes[1].p, (const float*)h->vels[0].p, (const float*)h->vels[1].p, h->pv, h->lb,
-                  (const double*)h->D.p, h->trial_part.p, h->nblk_vo, 0));
+                  (const double*)h->D.p, h->trial_part.p, h->nblk_vo, h->nblk_imu, 0));
     return (int)cudaGetLastError();
 }
 
@@ -800,7 +846,7 @@ static double* trial_sum_ptr(islam_pvgo* h) { return h->sums.p + 4; }
 
 // phase A: open the try, linearise if a new step starts, sum the loss partials, damp
 static int enqueue_open(islam_pvgo* h, cudaStream_t s) {
-    const int np_ = h->nblk_vo + h->nblk_imu;
+    const int np_ = h->n_blocks();
     CK(launch_pdl(k_begin_try, 1, 32, 0, s, h->st.p));
     int rc = launch_linearize(h, s, 0);
     if (rc) return rc;
@@ -819,7 +865,7 @@ static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
 
 // after the all-reduce of the shared panels (multi-GPU) / directly (single GPU): finish the solve, evaluate the trial
 static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
-    const int np_ = h->nblk_vo + h->nblk_imu;
+    const int np_ = h->n_blocks();
     int rc = 0;
     if (h->opts.n_parts > 1) {
         k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
@@ -836,7 +882,7 @@ static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
 }
 
 static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
-    const int np_ = h->nblk_vo + h->nblk_imu;
+    const int np_ = h->n_blocks();
     if (h->opts.n_parts > 1 && h->p2p)
         CK(launch_pdl(k_end_try_p2p, 1, 256, 0, s, h->st.p, (const islam_lm_params*)h->d_prm.p, (const double*)h->trial_part.p, np_,
                       trial_sum_ptr(h), (unsigned long long* const*)h->d_peers.p, h->mail_seq.p, h->opts.part, h->opts.n_parts));

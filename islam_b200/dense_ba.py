@@ -127,3 +127,39 @@ def scale_from_disp_flow(disp, flow, motion, fx, fy, cx, cy, baseline, depth=Non
     if int(cnt.item()) < 500:
         print('Warning! mask contains too less points!', int(cnt.item()))          # dense_ba.py:134-135
     return s.view(1), z[0], m[0], dm[0]
+
+
+def pixel2point(pixels, depth, intrinsics):
+    """dense_ba.py:9-64: pixels (...,N,2) with depth (...,N) -> camera-frame points (...,N,3)."""
+    assert pixels.size(-1) == 2 and depth.size(-1) == pixels.size(-2)
+    fx, fy = intrinsics[..., 0, 0], intrinsics[..., 1, 1]
+    cx, cy = intrinsics[..., 0, 2], intrinsics[..., 1, 2]
+    f = torch.stack([fx, fy], dim=-1).unsqueeze(-2)
+    c = torch.stack([cx, cy], dim=-1).unsqueeze(-2)
+    xy = (pixels - c) / f * depth.unsqueeze(-1)
+    return torch.cat([xy, depth.unsqueeze(-1)], dim=-1)
+
+
+class SparseReprojectionLoss:
+    """Mirror of dense_ba.py:276-305, the object `run_pvgo(..., reproj=...)` takes (pvgo.py:53-61,130-165): N sparse points per
+    consecutive pair, their 3-D positions in the first camera and their pixel targets (flow + pixel) in the second.
+    As a PVGO factor it is consumed by the fused kernels (csrc/linearize.cuh rp_block); called directly it evaluates the
+    residual (batch, N, 2) on the shim's LieTensor ops like the reference's __call__."""
+
+    def __init__(self, points2d, depth, flow, fx, fy, cx, cy, rgb2imu_pose, device='cuda:0'):
+        assert len(flow.shape) == 4 and len(depth.shape) == 3 and len(points2d.shape) == 3
+        bs, N = points2d.shape[:2]
+        idx = torch.cat([torch.arange(0, bs).repeat_interleave(N).view(bs, N, 1), _plain(points2d)[..., (1, 0)].cpu()], dim=-1).to(int)
+        points2d = _plain(points2d).to(device)
+        idx = idx.to(device)
+        depth, flow = _plain(depth).to(device), _plain(flow).to(device)
+        self.K = torch.tensor([fx, 0, cx, 0, fy, cy, 0, 0, 1], dtype=torch.float32).view(3, 3).to(device)
+        self.point3d = pixel2point(points2d, depth[idx[..., 0], idx[..., 1], idx[..., 2]].view(bs, N), self.K).to(device)
+        self.target = (flow.permute(0, 2, 3, 1)[idx[..., 0], idx[..., 1], idx[..., 2], :].view(bs, N, 2) + points2d).to(device)
+        self.N = N
+        self.rgb2imu_pose = rgb2imu_pose.to(device)
+
+    def __call__(self, motion):
+        from .pypose_compat.function.geometry import reprojerr
+        T = self.rgb2imu_pose.Inv() @ motion @ self.rgb2imu_pose
+        return reprojerr(self.point3d, self.target, self.K, T.Inv(), reduction='none')

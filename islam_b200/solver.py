@@ -45,6 +45,7 @@ class PVGOSolver:
         _lib.check(self.L.islam_pvgo_get_dims(self._h, C.byref(d)), 'islam_pvgo_get_dims')
         self.dims = d
         self.params = LMParams()
+        self.n_reproj = 0
         self.L.islam_lm_default_params(C.byref(self.params))
         # a private non-default stream: the LM loop is CUDA-graph captured, which the legacy stream cannot be
         self.stream = torch.cuda.Stream(device=self.device)
@@ -91,8 +92,34 @@ class PVGOSolver:
             t.record_stream(self.stream)
 
     def _set_reproj(self, reproj, loss_weight):
-        if reproj is not None:
-            raise NotImplementedError('the optional reprojection factor (pvgo.py:53-61) is not on the B200 path yet')
+        """The optional 5th residual group (pvgo.py:53-61): `reproj` is a SparseReprojectionLoss-shaped object (dense_ba.py:276-305:
+        attributes N, point3d (M,N,3), target (M,N,2), K (3,3), rgb2imu_pose SE3), information (loss_weight[4] / N)^2 (pvgo.py:131)."""
+        if reproj is None:
+            if self.n_reproj:
+                self._enter()
+                _lib.check(self.L.islam_pvgo_set_reproj(self._h, None, None, 0, None, None, 0.0, self._s()), 'islam_pvgo_set_reproj')
+                self.n_reproj = 0
+            return
+        for name in ('N', 'point3d', 'target', 'K', 'rgb2imu_pose'):
+            if not hasattr(reproj, name):
+                raise IslamError(f'reproj must look like dense_ba.SparseReprojectionLoss (missing `{name}`); the dense variant '
+                                 'cannot be a PVGO factor in the reference either (pvgo.py:131 needs reproj.N)')
+        if len(loss_weight) < 5:
+            raise IndexError('loss_weight needs a 5th entry when reproj is given (pvgo.py:131)')
+        n = int(reproj.N)
+        pts = _f32(reproj.point3d, self.device, (self.M, n, 3))
+        tgt = _f32(reproj.target, self.device, (self.M, n, 2))
+        K = torch.as_tensor(reproj.K).detach().cpu().to(torch.float32).reshape(3, 3)
+        intr = (C.c_float * 4)(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+        cal = reproj.rgb2imu_pose
+        cal = cal.detach().as_subclass(torch.Tensor) if isinstance(cal, torch.Tensor) else torch.as_tensor(np.asarray(cal))
+        c7 = (C.c_float * 7)(*[float(x) for x in cal.cpu().to(torch.float32).reshape(7)])
+        self._enter()
+        _lib.check(self.L.islam_pvgo_set_reproj(self._h, _ptr(pts), _ptr(tgt), n, C.byref(intr), C.byref(c7),
+                                                (float(loss_weight[4]) / n) ** 2, self._s()), 'islam_pvgo_set_reproj')
+        for t in (pts, tgt):
+            t.record_stream(self.stream)
+        self.n_reproj = n
 
     def set_state(self, nodes, vels):
         n = _f32(nodes, self.device, (self.N, 7))
@@ -114,10 +141,14 @@ class PVGOSolver:
         _lib.check(self.L.islam_pvgo_linearize(self._h, self._s()), 'islam_pvgo_linearize')
 
     def residuals(self):
-        """(pgerr (E,6), adjvelerr (M,3), imuroterr (M,3), transvelerr (M,3)) — pvgo.py:64 order."""
+        """(pgerr (E,6), adjvelerr (M,3), imuroterr (M,3), transvelerr (M,3)[, reprojerr (M, 2 N_points)]) — pvgo.py:61-64 order."""
         r = (self._new(self.E, 6), self._new(self.M, 3), self._new(self.M, 3), self._new(self.M, 3))
         _lib.check(self.L.islam_pvgo_get_residuals(self._h, *[_ptr(t) for t in r], self._s()),
                    'islam_pvgo_get_residuals')
+        if self.n_reproj:                       # pvgo.py:58-61: a 5th group, (M, 2 N_points)
+            rp = self._new(self.M, 2 * self.n_reproj)
+            _lib.check(self.L.islam_pvgo_get_reproj_residuals(self._h, _ptr(rp), self._s()), 'islam_pvgo_get_reproj_residuals')
+            r = r + (rp,)
         self._exit()
         return r
 

@@ -250,3 +250,28 @@ def window(seed=0, N=9):
     rng = np.random.default_rng(seed)
     gt, gv, _, _ = ground_truth(N)
     return _finish(f'win{N}', gt, gv, chain_links(N, 1), 0.1, rng, iters=10)
+
+
+def reproj_data(g, n_points=24, seed=0, sig_px=0.3, weight=2.0):
+    """Inputs of the optional sparse reprojection factor (/root/reference/pvgo.py:53-61, dense_ba.py:276-305) for graph g:
+    per consecutive pair, `n_points` 3-D points in the camera frame of pose i and their noisy pixel positions in the camera
+    at pose i+1 (ground-truth motion), a camera-to-body transform `rgb2imu` and pin-hole intrinsics (fx, fy, cx, cy).
+    Returns dict(point3d (M,N,3), target (M,N,2), K (4,), rgb2imu (7,), N, weight = loss_weight[4])."""
+    rng = np.random.default_rng(seed + 77)
+    M = g.N - 1
+    fx, fy, cx, cy = 80.0, 82.0, 79.5, 55.5
+    # camera looks along body x: camera z = body x, camera x = -body y, camera y = -body z (a usual rgb -> imu mounting) + offset
+    Rc = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    C = np.concatenate([[0.3, 0.05, -0.1], _q_from_R(Rc[None])[0]])
+    z = 4.0 + 26.0 * rng.random((M, n_points))
+    u = 160.0 * rng.random((M, n_points)); v = 112.0 * rng.random((M, n_points))
+    P = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], -1)
+    gt = g.gt_nodes.astype(np.float64)
+    motion = _se3_mul(_se3_inv(gt[:-1]), gt[1:])
+    T = _se3_mul(_se3_mul(_se3_inv(C)[None], motion), C[None])
+    Ti = _se3_inv(T)
+    Pc = _qrot(Ti[:, None, 3:], P) + Ti[:, None, :3]
+    tgt = np.stack([fx * Pc[..., 0] / Pc[..., 2] + cx, fy * Pc[..., 1] / Pc[..., 2] + cy], -1)
+    tgt = tgt + sig_px * rng.standard_normal(tgt.shape)
+    return dict(point3d=P.astype(np.float32), target=tgt.astype(np.float32), K=np.array([fx, fy, cx, cy], np.float32),
+                rgb2imu=C.astype(np.float32), N=n_points, weight=float(weight))

@@ -21,6 +21,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import lie
+from . import reproj_oracle
 
 
 # --------------------------------------------------------------------------------------------------
@@ -91,11 +92,17 @@ class _LMBase:
         self.last = None
         self.reject_count = 0
         self.history = []
+        # optional 5th residual group (pvgo.py:53-61): g.extra['reproj'] = dict(point3d, target, K, rgb2imu, N, weight)
+        self.rp = (getattr(g, 'extra', None) or {}).get('reproj')
+        self.w4 = (float(self.rp['weight']) / int(self.rp['N'])) ** 2 if self.rp is not None else 0.0     # pvgo.py:131
 
     # -- model --------------------------------------------------------------------------------------
     def _res(self):
-        return residuals(self.nodes, self.vels, self.edges, self.poses, self.drots, self.dtrans,
-                         self.dvels, self.dts)
+        res = residuals(self.nodes, self.vels, self.edges, self.poses, self.drots, self.dtrans,
+                        self.dvels, self.dts)
+        if self.rp is not None:
+            res = res + (reproj_oracle.residual(self.nodes, self.rp),)       # pvgo.py:58-61
+        return res
 
     def _update(self, dn, dv, sign=1.0):
         """update_parameter: nodes <- Exp(d) nodes ; vels <- vels + d  (A.1/A.4)."""
@@ -217,6 +224,9 @@ class DenseLM(_LMBase):
     """PyPose's dense algorithm, column layout [nodes 7N | vels 3N], rows [6E | 3M | 3M | 3M] (A.3/A.4)."""
 
     def dense_J(self, res):
+        if self.rp is not None:
+            raise NotImplementedError('the dense literal oracle covers the four residual groups train.py uses; '
+                                      'the reprojection factor is in SparseLM')
         N, E, M = self.N, self.E, self.M
         Jvo, Jrot = jacobian_blocks(self.nodes, self.vels, self.edges, self.poses, self.drots, res[0], res[2])
         R = 6 * E + 9 * M
@@ -328,9 +338,20 @@ class SparseLM(_LMBase):
         add_block(a, a, 0, 6, w3 * dI); add_block(a, a, 6, 0, w3 * dI)
         add_block(a, a, 6, 6, w3 * dI * dt[:, None, None])
         add_block(b, a, 0, 6, -w3 * dI); add_block(a, b, 6, 0, -w3 * dI)
+        Jrp = None
+        if self.rp is not None:
+            # reprojection: J(delta_i) = +Jrp, J(delta_{i+1}) = -Jrp (pair 0: zero), information w4 I
+            Jrp = reproj_oracle.jacobian(self.nodes, self.rp).astype(self.dtype)          # (M, 2Np, 6)
+            Sp = self.w4 * np.einsum('mki,mkj->mij', Jrp, Jrp)
+            add_block(a, a, 0, 0, Sp); add_block(b, b, 0, 0, Sp)
+            add_block(a, b, 0, 0, -Sp); add_block(b, a, 0, 0, -Sp)
         H = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                           shape=(9 * N, 9 * N), dtype=self.dtype).tocsc()
         g = np.zeros((N, 9), self.dtype)
+        if Jrp is not None:
+            qp = self.w4 * np.einsum('mki,mk->mi', Jrp, res[4])
+            g[:-1, 0:6] += qp; g[1:, 0:6] -= qp
+        self._Jrp = Jrp
         np.add.at(g[:, 0:6], j, q); np.add.at(g[:, 0:6], i, -q)
         g[1:, 3:6] += qr; g[:-1, 3:6] -= qr
         g[:-1, 6:9] += w1 * res[1]; g[1:, 6:9] -= w1 * res[1]
@@ -342,7 +363,7 @@ class SparseLM(_LMBase):
         H, g, Jvo, Jrot = self.assemble(res)
         d = H.diagonal().copy()
         d = np.clip(d, self.lm_min, self.lm_max).astype(self.dtype)
-        return dict(H=H, diag0=H.diagonal().copy(), diag=d, g=g, Jvo=Jvo, Jrot=Jrot)
+        return dict(H=H, diag0=H.diagonal().copy(), diag=d, g=g, Jvo=Jvo, Jrot=Jrot, Jrp=self._Jrp)
 
     def _damp(self, lin, damping):
         lin['diag'] = (lin['diag'] + lin['diag'] * self.dtype.type(damping)).astype(self.dtype)
@@ -385,6 +406,9 @@ class SparseLM(_LMBase):
         tot = 0.0
         for jd, r in zip((jd0, jd1, jd2, jd3), res):
             tot += float(np.sum(jd * (2 * r + jd)))
+        if lin.get('Jrp') is not None:
+            jd4 = np.einsum('mkj,mj->mk', lin['Jrp'], dn[:-1] - dn[1:])
+            tot += float(np.sum(jd4 * (2 * res[4] + jd4)))
         return -tot
 
 

@@ -48,9 +48,9 @@ def test_run_pvgo_imu_target_and_errors():
     ref = po.SparseLM(g, np.float64).run()
     a, b = ref.imu_loss()
     assert np.allclose(tl.cpu().numpy(), a, rtol=5e-3, atol=1e-8) and np.allclose(rl.cpu().numpy(), b, rtol=5e-3, atol=1e-9)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AttributeError):                             # pvgo.py:131 reads reproj.N
         run_pvgo(_t(g.init_nodes), _t(g.init_vels), _t(g.vo_motions), _t(g.links), _t(g.dts), _t(g.imu_drots),
-                 _t(g.imu_dtrans), _t(g.imu_dvels), reproj=object())
+                 _t(g.imu_dtrans), _t(g.imu_dvels), loss_weight=(1, 1, 1, 1, 1), reproj=object())
     with pytest.raises(Exception):                                  # len(dts) must be N-1 (pvgo.py:51 broadcast)
         run_pvgo(_t(g.init_nodes), _t(g.init_vels), _t(g.vo_motions), _t(g.links), _t(g.dts)[:-1], _t(g.imu_drots),
                  _t(g.imu_dtrans), _t(g.imu_dvels))

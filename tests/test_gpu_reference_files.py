@@ -10,11 +10,7 @@ Each result is compared with the repo's mirror (islam_b200.pvgo / .imu_integrato
 including the autograd of the outer losses into vo_motions (target='vo') and into imu_drots / imu_dvels (target='imu').
 This is INTEGRATION.md section B run for real: the residual definitions, weights, optimiser configuration and call order come
 from executing reference code, not from a restatement of it."""
-import hashlib
-import importlib
 import os
-import sys
-import types
 
 import numpy as np
 import pytest
@@ -22,10 +18,10 @@ import torch
 
 from islam_b200 import synth
 from oracle import imu_oracle, lie, pvgo_oracle as po
+from ref_loader import reference_modules
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SRC = os.path.join(HERE, 'golden', 'ref_src')
 GOLD = np.load(os.path.join(HERE, 'golden', 'imu_golden.npz'))
 DEV = 'cuda:0'
 
@@ -33,38 +29,8 @@ DEV = 'cuda:0'
 @pytest.fixture(scope='module')
 def ref():
     """(pvgo, imu_integrator, transformation, dense_ba) modules of the reference, imported unmodified over the shim."""
-    if not os.path.exists(os.path.join(REF_SRC, 'pvgo.py')):
-        pytest.skip('tests/golden/ref_src/ is not staged: run tests/golden/vendor_reference.py (or __graft_entry__.build()) '
-                    'in the build container, where /root/reference exists')
-    # the files executed are the files the vendoring script saw
-    want = dict(l.split()[::-1] for l in open(os.path.join(HERE, 'golden', 'ref_src.sha256')).read().splitlines())
-    for rel, digest in want.items():
-        assert hashlib.sha256(open(os.path.join(REF_SRC, rel), 'rb').read()).hexdigest() == digest, rel
-    import islam_b200.pypose_compat as ppc
-    ppc.install()
-    # imu_integrator.py:7 imports the CNN-GRU denoiser (a front-end network, out of scope); never instantiated here
-    net = types.ModuleType('Network')
-    den = types.ModuleType('Network.IMUDenoiseNet')
-    den.IMUCorrector_CNN_GRU_WO_COV = type('IMUCorrector_CNN_GRU_WO_COV', (), {})
-    net.IMUDenoiseNet = den
-    saved = {k: sys.modules.get(k) for k in ('Network', 'Network.IMUDenoiseNet', 'pvgo', 'imu_integrator', 'Datasets',
-                                              'Datasets.transformation', 'dense_ba')}
-    sys.modules['Network'], sys.modules['Network.IMUDenoiseNet'] = net, den
-    for k in ('pvgo', 'imu_integrator', 'Datasets', 'Datasets.transformation', 'dense_ba'):
-        sys.modules.pop(k, None)
-    sys.path.insert(0, REF_SRC)
-    try:
-        mods = (importlib.import_module('pvgo'), importlib.import_module('imu_integrator'),
-                importlib.import_module('Datasets.transformation'), importlib.import_module('dense_ba'))
-        assert os.path.dirname(mods[0].__file__) == REF_SRC
+    with reference_modules() as mods:
         yield mods
-    finally:
-        sys.path.remove(REF_SRC)
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
 
 
 def _inputs(g, pp, grad=None):
