@@ -164,6 +164,23 @@ int islam_pvgo_mailbox_connect(islam_pvgo* h, const void* handles /* n_parts x 6
  * -1 shared / replicated (solved redundantly on every rank) */
 int islam_pvgo_var_parts(const islam_pvgo* h, int32_t* out_host);
 
+/* ---- small-graph fast path: the whole run_pvgo of a window (pvgo.py:122-205) in ONE launch, one CTA per window --------
+ * For the window sizes train.py actually uses (run_kitti.sh:8: batch_size 8 => N = 9 poses): linearise, damp, dense banded
+ * float64 Cholesky in shared memory, solve, retract, trial loss, trust region, accept / roll back, StopOnPlateau, align_to
+ * and vo_loss (+ gradient) without leaving the SM.  B windows of identical structure (same N and edge list) per call.
+ * links_dev: E x 2 int32 on the device; links_host: the same as int64 on the host (validation, bandwidth).  All other
+ * pointers are device arrays, window-major: nodes0 B x N x 7, vels0 B x N x 3, vo_motions B x E x 7, imu_* B x (N-1) x ..,
+ * dts B x (N-1).  info_w: host, loss_weight^2 as islam_pvgo_set_problem.  Outputs: nodes / vels ALIGNED to each window's
+ * first initial pose (pvgo.py:195), one islam_lm_state per window, and — if trans_loss is given — vo_loss of `vo_P` (NULL:
+ * vo_motions itself) with its left-tangent gradients (nullable).  Supported: 2 <= N <= 16, E <= 128 (islam_pvgo_small_supported). */
+int islam_pvgo_small_supported(int32_t N, int32_t E);
+int islam_pvgo_small_run(int32_t B, int32_t N, int32_t E, const int32_t* links_dev, const int64_t* links_host,
+                         const float* nodes0, const float* vels0, const float* vo_motions, const float* imu_drots,
+                         const float* imu_dtrans, const float* imu_dvels, const float* dts, const double info_w[4],
+                         const islam_lm_params* params, float* nodes_out, float* vels_out, islam_lm_state* state_out /* device, B */,
+                         const float* vo_P, float* trans_loss /* B x E */, float* rot_loss, float* grad_trans /* B x E x 6 */,
+                         float* grad_rot, void* stream);
+
 /* ---- outer losses and gauge alignment ------------------------------------------------------------------ */
 /* vo_loss (pvgo.py:67-78) at the current nodes (detached) for arbitrary vo_motions P (E x 7):
  * trans_loss/rot_loss (E); if grad_* given: d loss_e / d(left tangent of P_e) (E x 6 each) */

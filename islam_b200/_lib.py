@@ -75,6 +75,9 @@ _SIGS = {
     'islam_pvgo_var_parts': (C.c_int, [_P, _P]),
     'islam_pvgo_mailbox_export': (C.c_int, [_P, _P]),
     'islam_pvgo_mailbox_connect': (C.c_int, [_P, _P]),
+    'islam_pvgo_small_supported': (C.c_int, [C.c_int32, C.c_int32]),
+    'islam_pvgo_small_run': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_double * 4),
+                                       C.POINTER(LMParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'islam_pvgo_vo_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'islam_pvgo_imu_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     'islam_pvgo_align': (C.c_int, [_P, _P, _P, _P, _P]),

@@ -13,6 +13,7 @@
 #include "lm.cuh"
 #include "solver3.cuh"
 #include "front4.cuh"
+#include "small.cuh"
 #include "symbolic.h"
 #include "symbolic3.h"
 

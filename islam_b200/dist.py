@@ -96,6 +96,29 @@ class ShardedPVGO:
                 self._allreduce(self.sums)
             _lib.check(s.L.islam_pvgo_lm_try_end(s._h, st), 'islam_pvgo_lm_try_end')
 
+    def _graph_try(self):
+        """One try as a CUDA graph: ~25 kernels of the library (with their programmatic dependent launches) AND the NCCL
+        all-reduce between them, captured once on the solver's stream and replayed — the single-GPU path has always
+        replayed a graph (islam_pvgo_lm_run); the sharded one used to enqueue every kernel from Python through three ctypes
+        calls around torch.distributed.  All control state lives on the device, so the captured arguments never change.
+        Falls back to eager enqueueing with the gloo test rig (host-staged collectives cannot be captured)."""
+        if not self._nccl or self._graph is False:
+            return None
+        if self._graph is None:
+            try:
+                self.lm_try()                                   # warm-up outside capture (NCCL channel set-up, lazy allocations)
+                torch.cuda.synchronize(self.s.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.s.stream, capture_error_mode='thread_local'):
+                    self.lm_try()
+                self._graph = g
+            except Exception:                                   # capture not possible in this environment: stay eager
+                self._graph = False
+                return None
+        return self._graph
+
+    _graph = None
+
     def lm_run(self, budget=None):
         """The `while scheduler.continual()` loop: tries are enqueued back to back (device-side predicates make
         surplus tries no-ops); one synchronisation at the end, more only if rejected tries exhaust the budget."""
@@ -103,20 +126,27 @@ class ShardedPVGO:
         s._enter()
         if budget is None:                      # same policy as islam_pvgo_lm_run
             budget = min(s.params.max_steps + 2, 4) if s.params.use_scheduler else s.params.max_steps + 2
+        g = self._graph_try() if self.use_graph else None
         for _ in range(64):
             for _ in range(budget):
-                self.lm_try()
+                if g is not None:
+                    with torch.cuda.stream(s.stream):
+                        g.replay()
+                else:
+                    self.lm_try()
             st = s.lm_state()
             if not st.continual:
                 return st
             budget = 4
         return st
 
+    use_graph = True
+
     def get_state(self):
-        """Each pose is taken from the rank that solves it (shared poses from rank 0) and summed across ranks."""
+        """Each pose is taken from the rank that solves it (shared poses from rank 0): ONE all-reduce of the packed
+        (N, 10) state whose foreign rows are zeroed."""
         n, v = self.s.get_state()
-        n = torch.where(self._mine_pose.unsqueeze(-1), n, torch.zeros_like(n))
-        v = torch.where(self._mine_vel.unsqueeze(-1), v, torch.zeros_like(v))
-        self._allreduce(n)
-        self._allreduce(v)
-        return n, v
+        packed = torch.cat([torch.where(self._mine_pose.unsqueeze(-1), n, torch.zeros_like(n)),
+                            torch.where(self._mine_vel.unsqueeze(-1), v, torch.zeros_like(v))], dim=1)
+        self._allreduce(packed)
+        return packed[:, :7].contiguous(), packed[:, 7:].contiguous()

@@ -210,6 +210,56 @@ class PoseVelGraph(torch.nn.Module):
         return _wrap_like(self._nodes_ref, n, 'SE3_type'), v
 
 
+def _small_ok(n_nodes, n_links):
+    import os
+    if os.environ.get('ISLAM_NO_SMALL') == '1':
+        return False
+    from . import _lib
+    return bool(_lib.lib().islam_pvgo_small_supported(int(n_nodes), int(n_links)))
+
+
+def _run_small(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels, device, radius, loss_weight,
+               max_steps, patience, decreasing, use_scheduler, batch=None):
+    from . import small
+    N = init_nodes.shape[-2]
+    B = 1 if batch is None else batch
+    r = small.get_runner(N, links, device, B)
+    P = _plain(vo_motions)
+    need_grad = P.requires_grad and torch.is_grad_enabled()
+    args = dict(nodes0=init_nodes, vels0=init_vels, Z=P, drot=imu_drots, dtrans=imu_dtrans, dvel=imu_dvels, dt=dts)
+    states, nodes, vels, tl, rl, gt, gr = r.run(args, loss_weight, vo_P=None, with_grad=need_grad, radius=float(radius), lm_min=1e-4,
+                                                max_steps=int(max_steps), patience=int(patience), decreasing=float(decreasing),
+                                                use_scheduler=1 if use_scheduler else 0)
+    for st in states:
+        if st.info == 1:
+            print('Linear solver failed. Breaking optimization step...')        # PyPose's message (A.4)
+    if need_grad:
+        Pd = P.to(device=r.device, dtype=torch.float32).reshape(B, -1, 7)         # differentiable: the gradient reaches the caller's tensor
+        tl, rl = small.PrecomputedVoLoss.apply(Pd, tl, rl, gt, gr)
+    if batch is None:
+        nodes, vels, tl, rl = nodes[0], vels[0], tl[0], rl[0]
+        run_pvgo.last_state = states[0]
+    else:
+        run_pvgo_batch.last_states = states
+    return tl, rl, _wrap_like(init_nodes, nodes, 'SE3_type'), vels
+
+
+def run_pvgo_batch(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels, device='cuda:0', radius=1e4,
+                   loss_weight=(1, 1, 1, 1), max_steps=10, patience=3, decreasing=1e-3, use_scheduler=True):
+    """B independent windows of identical structure in ONE launch, one CTA per window: init_nodes (B,N,7), init_vels (B,N,3),
+    vo_motions (B,E,7), links (E,2) shared, dts (B,N-1), imu_* (B,N-1,.).  Returns (trans_loss (B,E), rot_loss (B,E),
+    nodes (B,N,7) cpu, vels (B,N,3) cpu): what B calls of run_pvgo (pvgo.py:122-205, target='vo') return, stacked.
+    (train.py optimises its windows one after the other only because each is initialised from the previous one; windows that
+    are independent — several sequences, or a re-run over stored initial states — batch.)"""
+    if not torch.cuda.is_available():
+        raise IslamError('run_pvgo_batch needs a CUDA device: there is no CPU fallback')
+    B, N = init_nodes.shape[0], init_nodes.shape[1]
+    if not _small_ok(N, len(links)):
+        raise IslamError('run_pvgo_batch covers windows of up to 16 poses / 128 edges; use run_pvgo for larger graphs')
+    return _run_small(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels, device, radius, loss_weight,
+                      max_steps, patience, decreasing, use_scheduler, batch=B)
+
+
 def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels,
              device='cuda:0', radius=1e4, loss_weight=(1, 1, 1, 1), reproj=None, target='vo',
              max_steps=10, patience=3, decreasing=1e-3, use_scheduler=True):
@@ -225,6 +275,14 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
     transvel_infos = np.ones(n_nodes - 1) * loss_weight[3] ** 2
     if reproj is not None:
         reproj_infos = np.ones(n_nodes - 1) * (loss_weight[4] / reproj.N) ** 2        # pvgo.py:130-131
+
+    if reproj is None and target == 'vo' and _small_ok(n_nodes, n_links):
+        # the window sizes train.py uses (run_kitti.sh:8): the whole call is ONE kernel launch (csrc/small.cuh)
+        out = _run_small(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtrans, imu_dvels, device, radius,
+                         loss_weight, max_steps, patience, decreasing, use_scheduler)
+        covs = {'vo_rot': vo_rot_infos, 'imu_rot': imu_rot_infos, 'vo_trans': vo_trans_infos,
+                'imu_vel': imu_vel_infos, 'transvel': transvel_infos}           # pvgo.py:199-203
+        return out + (covs,)
 
     graph = PoseVelGraph(init_nodes, init_vels, reproj, links=links, device=device)
     # one host -> device transfer of the VO motions serves both the optimisation (detached, pvgo.py:146) and the outer
