@@ -337,6 +337,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         _emit(out)
     if world > 1:
+        sh.release_graph()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -533,8 +533,11 @@ assemble_pairs_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
     bool adj = av.pair_adj[p] && (pv.pair_owner == nullptr || pv.pair_owner[lo] == pv.part);
     const float* Jr = lb.J_rot + 9 * (size_t)lo;
     double dt = adj ? (double)pv.dt[lo] : 0.0;
-    for (int idx = lane; idx < 81; idx += 32) {
-        int a = idx / 9, b = idx - 9 * a;
+    // a pair that is not an IMU pair only couples the 6 x 6 pose parts: its velocity rows / columns are structural zeros
+    // (zeroed once at creation, never read by the fronts) and are not rewritten every linearisation
+    const bool imu_pair = av.pair_adj[p] != 0;
+    for (int idx = lane; idx < (imu_pair ? 81 : 36); idx += 32) {
+        int a = imu_pair ? idx / 9 : idx / 6, b = imu_pair ? idx - 9 * a : idx - 6 * a;
         double v = 0.0;
         if (a < 6 && b < 6) {
             for (int k = e0; k < e1; ++k) {
@@ -557,7 +560,7 @@ assemble_pairs_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
             if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w[3] * dt;   // (v_lo, tau_hi)
             if (pv.rp_n > 0 && a < 6 && b < 6) v -= pv.w[4] * lb.S_rp[36 * (size_t)lo + 6 * a + b];
         }
-        Ho[81 * (size_t)p + idx] = v;
+        Ho[81 * (size_t)p + 9 * a + b] = v;
     }
 }
 

@@ -169,6 +169,9 @@ __global__ void k_set_state_flags(LMState* st, int cur) {
 
 }  // namespace
 
+// persisting-L2 window of a launch (see launch_pdl_w)
+struct L2Window { const void* base = nullptr; size_t bytes = 0; };
+
 // =================================================================================================================
 struct islam_pvgo {
     Plan plan;                      // pairs / CSR for the assembly kernels
@@ -214,6 +217,7 @@ struct islam_pvgo {
     // dynamic shared memory of the factor / back-substitution kernels
     std::vector<int> level_variant, level_smem_bytes, level_bs_bytes, level_count;
     std::vector<int> level_front4;          // 1: the level runs the pipelined front kernel (front4.cuh)
+    L2Window win_U, win_L;                   // persisting-L2 windows of the factor / back-substitution launches (empty: off)
     int n_sm = 148;
     // multi-GPU: per level, the contiguous [local | shared] split of level_fronts
     std::vector<int> level_nlocal, level_nshared;
@@ -396,8 +400,24 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         cudaMemset(h->shared.p, 0, sizeof(double) * h->shared_doubles);
     }
     AL(Lbuf, (size_t)q.L_doubles); AL(Ubuf, (size_t)q.U_doubles); AL(Linv, (size_t)std::max(1LL, q.I_doubles));
+    {
+        // persisting L2, opt-in (ISLAM_L2_PERSIST=1): set aside as much as the device allows and mark U (factorisation) and L
+        // (back-substitution) as the windows.  Measured on C2 (profiles/r02_l2_persist.txt): DRAM traffic of a try drops, the try
+        // does not get faster (it is latency-bound, 2 079 vs 2 119 LM it/s), so the default stays off.
+        const char* e = std::getenv("ISLAM_L2_PERSIST");
+        int dev = 0, max_persist = 0, max_win = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (e && e[0] == '1' && max_persist > 0 && max_win > 0 && q.dense_root < 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            h->win_U.base = h->Ubuf.p; h->win_U.bytes = std::min<size_t>(sizeof(double) * (size_t)q.U_doubles, (size_t)max_win);
+            h->win_L.base = h->Lbuf.p; h->win_L.bytes = std::min<size_t>(sizeof(double) * (size_t)q.L_doubles, (size_t)max_win);
+        }
+    }
     AL(st, 1); AL(d_prm, 1); AL(d_w, 5);
     cudaMemset(h->D.p, 0, sizeof(double) * 9 * (size_t)N);
+    cudaMemset(h->Ho.p, 0, sizeof(double) * 81 * (size_t)p.P);      // structural zeros of the non-IMU pairs are never rewritten
     if (cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) { delete h; return -1; }
 #undef UP
 #undef AL
@@ -630,15 +650,34 @@ extern "C" int islam_pvgo_get_state(islam_pvgo* h, float* nodes, float* vels, vo
 // ---- launch helpers ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: the kernel may start (and run up to its cudaGridDependencySynchronize()) while the
 // previous kernel in the stream is still draining.
+// An optional L2 access-policy window travels with the launch (and into the captured graph's kernel node): the update
+// matrices (written by one level, read once by the next) and the factor (written by the factorisation, read by the
+// back-substitution) are marked persisting so that they stay in the 126 MB L2 instead of making a round trip through HBM.
+static L2Window g_no_window;
+
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+static cudaError_t launch_pdl_w(const L2Window& win, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s,
+                                Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (win.base != nullptr && win.bytes > 0) {
+        at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(win.base);
+        at[1].val.accessPolicyWindow.num_bytes = win.bytes;
+        at[1].val.accessPolicyWindow.hitRatio = 1.0f;
+        at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+    return launch_pdl_w(g_no_window, kern, grid, block, smem, s, args...);
 }
 
 // kernel family 1 in two launches: all factors (residuals, Jacobian blocks, per-factor J^T W J), then the deterministic
@@ -678,12 +717,12 @@ static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int
     const size_t smem = (size_t)h->level_smem_bytes[l];
     const int var = h->level_variant[l];
     if (stage == 0 && h->level_front4[l])
-        return launch_pdl(k_front4<F4_NT>, n, F4_NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), h->fm,
+        return launch_pdl_w(h->win_U, k_front4<F4_NT>, n, F4_NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), h->fm,
                           (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p,
                           q.lm_min, q.lm_max, forced_scale, pre_ok, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p,
                           (int)(smem / sizeof(double)));
 #define F3_LAUNCH(NT, MINB, US)                                                                                          \
-    launch_pdl(k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
+    launch_pdl_w(h->win_U, k_factor3<NT, MINB, US>, n, NT, smem, s, (const LMState*)h->st.p, (const int*)(h->d_level_fronts.p + first), \
                h->fm, (const double*)h->Hd.p, (const double*)h->Ho.p, (const double*)h->g.p, h->Lbuf.p, h->Ubuf.p, h->Linv.p, \
                h->shared.p, q.lm_min, q.lm_max, forced_scale, stage, pre_ok, trigger_early, &h->st.p->chol_fail, (const islam_lm_params*)h->d_prm.p)
     switch (var) {
@@ -763,7 +802,7 @@ static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
     // top of the tree: one launch, parents first, fronts chained through completion counters (solver3.cuh)
     int first_separate = p.n_levels - 1;
     if (h->bs_chain_n > 0) {
-        CK(launch_pdl(k_backsolve3, h->bs_chain_n, BS3_THREADS, (size_t)h->bs_chain_bytes, s, (const LMState*)h->st.p,
+        CK(launch_pdl_w(h->win_L, k_backsolve3, h->bs_chain_n, BS3_THREADS, (size_t)h->bs_chain_bytes, s, (const LMState*)h->st.p,
                       (const int*)h->d_bs_chain.p, h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p, h->D.p, force,
                       h->bs_chain_bytes / 8, h->bs_chain_late, 1, h->d_bs_count.p, p.dense_root));
         first_separate = h->bs_chain_from - 1;
@@ -772,7 +811,7 @@ static int launch_backsolve(islam_pvgo* h, cudaStream_t s, int force) {
         int n = h->level_nlocal[l] + h->level_nshared[l];
         if (!n) continue;
         const int n_late = (h->bs_chain_n == 0 && l == p.n_levels - 1) ? n : 0;
-        CK(launch_pdl(k_backsolve3, n, BS3_THREADS, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
+        CK(launch_pdl_w(h->win_L, k_backsolve3, n, BS3_THREADS, (size_t)h->level_bs_bytes[l], s, (const LMState*)h->st.p,
                       (const int*)(h->d_level_fronts.p + p.level_off[l]), h->fm, (const double*)h->Lbuf.p, (const double*)h->Linv.p,
                       h->D.p, force, h->level_bs_bytes[l] / 8, n_late, 0, h->d_bs_count.p, p.dense_root));
     }
