@@ -19,8 +19,8 @@
  *   - Every call takes the cudaStream_t to enqueue on (as void*), is asynchronous unless stated, and is
  *     CUDA-graph capturable except the functions marked "synchronises".
  *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.  islam_pvgo_create: -2 bad edge list,
- *     -5 boundary too wide for the back-substitution kernel, -6 dense loop-closure root with n_parts > 1 (the dense
- *     root is single-GPU), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
+ *     -5 boundary too wide for the back-substitution kernel, -6 a single-GPU-only call on an n_parts > 1 handle
+ *     (islam_pvgo_lm_try / _lm_run / _solve / _profile_try / _set_reproj), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
  *     islam_pvgo_lm_step / _lm_run: -9 the step / loop did not close within its worst-case try budget.
  *     LM state `info`: 1 Cholesky failed (PyPose's "Linear solver failed"), 2 a multi-GPU peer never answered, 3 a device-side
  *     wait inside the back-substitution timed out (wedged device); 2 and 3 also clear `continual`.
@@ -156,6 +156,25 @@ int islam_pvgo_shared_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles
 int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream);
 int islam_pvgo_sums_buffer(islam_pvgo* h, double** dev_ptr, int64_t* n_doubles);
 int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
+/* multi-GPU with a DENSE root (BASELINE config 4: thousands of loop closures; csrc/dense_root.cuh): the root is factored
+ * by all ranks together, 1-D block-column-cyclic over 128-column tile columns.  The try becomes
+ *   try_begin : ... as above, plus this rank's share of the root (its factors' blocks, its subtrees' update matrices)
+ *   -> all-reduce(SUM) of the shared buffer, of R (ld * n doubles) and of diag (n doubles: the original diagonal, whose
+ *      clamp is not linear, travels apart)
+ *   try_mid   : shared fronts, then the root's clamped + damped diagonal; returns BEFORE the root is factored
+ *   for k0 = 0, block, 2 block ... < n:
+ *       islam_pvgo_root_panel(k0)                       (a no-op except on islam_pvgo_root_owner(k0))
+ *       -> broadcast of R[k0 * ld, (k0 + min(block, n - k0)) * ld) from that owner (the factored block column)
+ *       islam_pvgo_root_update(k0)                      (trailing update of this rank's tile columns)
+ *   try_mid2  : root back-substitution (replicated), the window's back-substitution, retract, trial residuals
+ *   try_end   : as above.
+ * islam_pvgo_root_buffers returns n == 0 when the graph has no dense root or n_parts == 1 (then try_mid does it all and
+ * try_mid2 / root_panel / root_update return -1). */
+int islam_pvgo_root_buffers(islam_pvgo* h, double** R, int64_t* n, int64_t* ld, double** diag, int32_t* block);
+int islam_pvgo_root_owner(const islam_pvgo* h, int64_t k0);
+int islam_pvgo_root_panel(islam_pvgo* h, int64_t k0, void* stream);
+int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream);
+int islam_pvgo_lm_try_mid2(islam_pvgo* h, void* stream);
 /* peer mailboxes: every rank exports the IPC handle of its mailbox (64 bytes), the caller all-gathers them (rank order)
  * and hands the table to every rank.  LM state info = 2 reports a peer that never answered (2 s timeout). */
 int islam_pvgo_mailbox_export(islam_pvgo* h, void* handle_out /* 64 bytes */);

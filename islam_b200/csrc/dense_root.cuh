@@ -31,7 +31,9 @@ struct RootView {
 __global__ void __launch_bounds__(128)
 k_root_orig(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Hd,
             const double* __restrict__ Ho, const double* __restrict__ g, const islam_lm_params* __restrict__ prm,
-            double forced_scale, double lm_min_, double lm_max_) {
+            double forced_scale, double lm_min_, double lm_max_, double* __restrict__ diag_out) {
+    // diag_out != nullptr (multi-GPU): this rank only holds ITS factors' share of the normal equations, so the diagonal,
+    // whose clamp is non-linear, is summed apart (k_root_diag adds it after the all-reduce)
     if (forced_scale == 0.0 && !st->active) return;
     const double scale = forced_scale != 0.0 ? forced_scale : st->diag_scale;
     const double lm_min = forced_scale != 0.0 ? lm_min_ : prm->lm_min, lm_max = forced_scale != 0.0 ? lm_max_ : prm->lm_max;
@@ -43,7 +45,10 @@ k_root_orig(const LMState* __restrict__ st, RootView rv, Front3Meta m, const dou
         if (rs == cs && r < c) return;
         const double* arr = (src & 2) ? Ho : Hd;
         double v = arr[(size_t)(src >> 2) + ((src & 1) ? 9 * c + r : 9 * r + c)];
-        if (rs == cs && r == c) v = fmin(fmax(v, lm_min), lm_max) * scale;
+        if (rs == cs && r == c) {
+            if (diag_out) { atomicAdd(&diag_out[3 * rs + r], v); return; }
+            v = fmin(fmax(v, lm_min), lm_max) * scale;
+        }
         atomicAdd(&rv.R[(3 * rs + r) + (size_t)(3 * cs + c) * rv.ld], v);
     } else if (idx < 9 * no + rv.n) {
         const int j = idx - 9 * no;
@@ -51,12 +56,24 @@ k_root_orig(const LMState* __restrict__ st, RootView rv, Front3Meta m, const dou
     }
 }
 
-// extend-add of the children's (packed) update matrices, one CTA per child
+// multi-GPU: the summed original diagonal, clamped and damped like k_root_orig does on one GPU
+__global__ void __launch_bounds__(128)
+k_root_diag(const LMState* __restrict__ st, RootView rv, const double* __restrict__ diag, const islam_lm_params* __restrict__ prm) {
+    if (!st->active) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < rv.n) rv.R[j + (size_t)j * rv.ld] += fmin(fmax(diag[j], prm->lm_min), prm->lm_max) * st->diag_scale;
+}
+
+// extend-add of the children's (packed) update matrices, one CTA per child.  want_part: ROOT_ALL_CHILDREN, or only the
+// children of that pose window (multi-GPU: the rank's own before the all-reduce, -1 = the shared separators after it)
+constexpr int ROOT_ALL_CHILDREN = -2;
 __global__ void __launch_bounds__(256)
-k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Ubuf, int force) {
+k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Ubuf, int force,
+                int want_part) {
     if (!force && !st->active) return;
     const int k = rv.children[blockIdx.x];
     const int c = m.children[k];
+    if (want_part != ROOT_ALL_CHILDREN && m.part[c] != want_part) return;
     const int* cm = m.cmap + m.cmap_off[k];
     const int ub = 3 * m.nb[c] + 1;
     const double* U = Ubuf + m.Uoff[c];
@@ -143,19 +160,35 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Tiles sit on the ABSOLUTE 128-grid of the matrix (entries left of / above `base` = k0 + nbk are masked), so that a tile
+// column has one owner for the whole factorisation: with G ranks, rank r updates the tile columns tc with tc % G == r
+// (1-D block-column-cyclic; G = 1 on a single GPU).  The grid enumerates this rank's tiles only.
+__host__ __device__ inline long long root_syrk_tiles(int n, int base, int G, int rank, int* T_out, int* j0_out) {
+    const int tc0 = base / SY_T;                                 // first tile column / row with anything to update
+    const int T = (n + 1 + SY_T - 1) / SY_T - tc0;               // tile rows (down to the rhs row) below / at tc0
+    const int Tc = (n + SY_T - 1) / SY_T - tc0;                  // tile columns
+    int j0 = ((rank - tc0) % G + G) % G;                         // first owned column, relative to tc0
+    if (T_out) *T_out = T;
+    if (j0_out) *j0_out = j0;
+    long long total = 0;
+    for (int j = j0; j < Tc; j += G) total += T - j;
+    return total;
+}
+
 __global__ void __launch_bounds__(256)
-k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force) {
+k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int force, int G, int rank) {
     if (!force && !st->active) return;
     extern __shared__ __align__(16) double sm_syrk[];
     double* As = sm_syrk;                      // [k][row], row stride SY_LD
     double* Bs = sm_syrk + DR_NB * SY_LD;
-    const int t = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while ((long long)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while ((long long)ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - (int)((long long)ti * (ti + 1) / 2);
     const int base = k0 + nbk;
-    const int r0 = base + SY_T * ti, c0 = base + SY_T * tj;
+    int T, tj;
+    root_syrk_tiles(rv.n, base, G, rank, &T, &tj);
+    int t = blockIdx.x;
+    while (t >= T - tj) { t -= T - tj; tj += G; }          // at most (tile columns / G) steps
+    const int ti = tj + t;
+    const int tile0 = (base / SY_T) * SY_T;
+    const int r0 = tile0 + SY_T * ti, c0 = tile0 + SY_T * tj;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nbk4 = (nbk + 3) & ~3;
     // operand panels: asynchronous 8-byte copies global -> shared (no register staging, all of them in flight at once);
@@ -172,7 +205,8 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int fo
     }
     asm volatile("cp.async.commit_group;");
     const int wr = 32 * (w & 3), wc = 64 * (w >> 2);       // this warp's 32 x 64 piece of the tile
-    const bool idle = ti == tj && wr + 31 < wc;             // entirely above the diagonal
+    // entirely above the diagonal, or entirely left of / above `base` (already final)
+    const bool idle = (ti == tj && wr + 31 < wc) || c0 + wc + 64 <= base || r0 + wr + 32 <= base;
     const int lk = lane & 3, lm = lane >> 2;
     // the accumulators start as the C tile itself (its loads overlap the panel copies) and the A fragments are negated:
     // D = (-A) B + C, so the result is stored without a dependent read-modify-write at the end
@@ -185,7 +219,7 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int fo
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = c0 + wc + 8 * j + 2 * lk + e;
-                acc[i][j][e] = (!idle && r <= rv.n && c < rv.n && r >= c) ? rv.R[r + (size_t)c * rv.ld] : 0.0;
+                acc[i][j][e] = (!idle && r <= rv.n && c < rv.n && r >= c && c >= base) ? rv.R[r + (size_t)c * rv.ld] : 0.0;
             }
     }
     asm volatile("cp.async.wait_group 0;");
@@ -213,7 +247,7 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nbk, int fo
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = c0 + wc + 8 * j + 2 * lk + e;
-                if (c < rv.n && r >= c) rv.R[r + (size_t)c * rv.ld] = acc[i][j][e];
+                if (c < rv.n && r >= c && c >= base) rv.R[r + (size_t)c * rv.ld] = acc[i][j][e];
             }
     }
 }

@@ -196,7 +196,7 @@ struct islam_pvgo {
         d_orig_cs, d_orig_src, d_part, d_level_fronts, d_shared_fronts, d_root_vars, d_root_children, d_parent, d_bs_chain,
         d_bs_count;
     DevBuf<long long> d_Loff, d_Uoff, d_Ioff, d_shared_off;
-    DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x;
+    DevBuf<double> Lbuf, Ubuf, Linv, shared, root_x, root_diag;
     DevBuf<unsigned short> d_dmap;
     // multi-GPU: peer mailboxes for the trial sums (k_end_try_p2p)
     DevBuf<unsigned long long> mail, mail_seq;
@@ -205,6 +205,7 @@ struct islam_pvgo {
     bool p2p = false;
     RootView rv;
     bool has_root = false;
+    bool root_dist() const { return has_root && opts.n_parts > 1; }      // dense root factored block-column-cyclically over the ranks
     DevBuf<LMState> st;
     DevBuf<islam_lm_params> d_prm;
     DevBuf<double> d_w;
@@ -243,7 +244,7 @@ struct islam_pvgo {
         DevBuf<float>* fb[] = {&Z, &drot, &dtrans, &dvel, &dt, &nodes[0], &nodes[1], &vels[0], &vels[1], &r_vo, &J_vo,
                                &r_imu, &J_rot, &rp_pts, &rp_tgt, &rp_cal, &r_rp};
         for (auto* b : fb) b->release();
-        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x,
+        DevBuf<double>* db[] = {&S_vo, &q_vo, &lin_part, &trial_part, &sums, &Hd, &Ho, &g, &D, &Lbuf, &Ubuf, &Linv, &shared, &root_x, &root_diag,
                                 &S_rp, &q_rp};
         for (auto* b : db) b->release();
         d_Loff.release(); d_Uoff.release(); d_Ioff.release(); d_shared_off.release(); d_dmap.release();
@@ -294,7 +295,6 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
     const Plan3& q = h->p3;
     // Loop-closure endpoints are eliminated last; from 33 closure poses on they form ONE dense root (dense_root.cuh).
     if (q.U_doubles + q.L_doubles > (1LL << 34)) { delete h; return -7; }       // > 128 GB of fp64 panels
-    if (q.dense_root >= 0 && opts.n_parts > 1) { delete h; return -6; }          // dense root: single GPU only for now
     islam_lm_default_params(&h->prm);
 
 #define UP(buf, vec) do { cudaError_t _e = h->buf.upload(vec); if (_e != cudaSuccess) { delete h; return (int)_e; } } while (0)
@@ -535,6 +535,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         cudaError_t e1 = h->d_root_vars.upload(rvars);
         if (e1 == cudaSuccess) e1 = h->d_root_children.upload(kids);
         if (e1 == cudaSuccess) e1 = h->root_x.alloc(3 * (size_t)K + 1);
+        if (e1 == cudaSuccess && opts.n_parts > 1) e1 = h->root_diag.alloc(3 * (size_t)K);      // multi-GPU: summed apart, then clamped
         if (e1 != cudaSuccess) { delete h; return (int)e1; }
         RootView& rv = h->rv;
         rv.R = h->Lbuf.p + q.f_Loff[fr]; rv.n = 3 * K; rv.ld = 3 * K + 1; rv.K = K; rv.front = fr;
@@ -705,6 +706,7 @@ static int launch_trial(islam_pvgo* h, cudaStream_t s) {
 
 static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale);
 static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force);
+static int launch_root_finish(islam_pvgo* h, cudaStream_t s);
 
 // `n` fronts of level l starting at d_level_fronts[first], in the given stage (solver3.cuh)
 static cudaError_t launch_factor_level(islam_pvgo* h, cudaStream_t s, int l, int first, int n, double forced_scale, int stage,
@@ -747,6 +749,27 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
 }
 
 // ---- dense root: tiled right-looking Cholesky of the loop-closure Schur complement, then its back-substitution ----------
+// one block column of the right-looking factorisation: diagonal block + the panel below (the tile column's owner only) ...
+static int launch_root_panel(islam_pvgo* h, cudaStream_t s, int k0, int force) {
+    const RootView& rv = h->rv;
+    const int G = h->opts.n_parts, nbk = std::min(DR_NB, rv.n - k0);
+    if ((k0 / SY_T) % G != h->opts.part) return 0;
+    k_root_potrf<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, force, &h->st.p->chol_fail);
+    const int below = rv.n + 1 - (k0 + nbk);                      // rows below, including the rhs row
+    if (below > 0)
+        k_root_trsm<<<(below + 127) / 128, 128, sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128), s>>>(h->st.p, rv, k0, nbk, force);
+    return (int)cudaGetLastError();
+}
+// ... and the trailing update with it, on this rank's tile columns
+static int launch_root_update(islam_pvgo* h, cudaStream_t s, int k0, int force) {
+    const RootView& rv = h->rv;
+    const int nbk = std::min(DR_NB, rv.n - k0);
+    if (k0 + nbk >= rv.n) return 0;
+    const long long ntiles = root_syrk_tiles(rv.n, k0 + nbk, h->opts.n_parts, h->opts.part, nullptr, nullptr);
+    if (ntiles > 0) k_root_syrk<<<(unsigned)ntiles, 256, SY_SMEM, s>>>(h->st.p, rv, k0, nbk, force, h->opts.n_parts, h->opts.part);
+    return (int)cudaGetLastError();
+}
+
 static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
     if (!h->has_root) return 0;
     const RootView& rv = h->rv;
@@ -755,20 +778,31 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
     CK(cudaMemsetAsync(rv.R, 0, sizeof(double) * (size_t)rv.ld * rv.n, s));
     const Plan3& p = h->p3;
     const int tasks = 9 * (p.f_orig_off[rv.front + 1] - p.f_orig_off[rv.front]) + rv.n;
-    k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min, q.lm_max);
-    if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force);
-    for (int k0 = 0; k0 < rv.n; k0 += DR_NB) {
-        int nbk = std::min(DR_NB, rv.n - k0);
-        k_root_potrf<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, force, &h->st.p->chol_fail);
-        int below = rv.n + 1 - (k0 + nbk);                      // rows below, including the rhs row
-        if (below > 0)
-            k_root_trsm<<<(below + 127) / 128, 128, sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128), s>>>(h->st.p, rv, k0, nbk, force);
-        if (k0 + nbk < rv.n) {
-            long long T = (below + SY_T - 1) / SY_T;
-            long long ntiles = T * (T + 1) / 2;
-            k_root_syrk<<<(unsigned)ntiles, 256, SY_SMEM, s>>>(h->st.p, rv, k0, nbk, force);
-        }
+    if (h->root_dist()) {
+        // multi-GPU, before the all-reduce: this rank's share of the root (its factors' blocks, its subtrees' update matrices)
+        CK(cudaMemsetAsync(h->root_diag.p, 0, sizeof(double) * rv.n, s));
+        k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min,
+                                                        q.lm_max, h->root_diag.p);
+        if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, h->opts.part);
+        return (int)cudaGetLastError();
     }
+    k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min,
+                                                    q.lm_max, (double*)nullptr);
+    if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, ROOT_ALL_CHILDREN);
+    for (int k0 = 0; k0 < rv.n; k0 += DR_NB) {
+        int rc = launch_root_panel(h, s, k0, force);
+        if (!rc) rc = launch_root_update(h, s, k0, force);
+        if (rc) return rc;
+    }
+    return (int)cudaGetLastError();
+}
+
+// multi-GPU, after the all-reduce of the root and of the shared panels: the shared separators' update matrices (every rank
+// factors those redundantly) and the clamped + damped diagonal
+static int launch_root_finish(islam_pvgo* h, cudaStream_t s) {
+    const RootView& rv = h->rv;
+    if (rv.nchildren && h->n_shared > 0) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, 0, -1);
+    k_root_diag<<<(rv.n + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->root_diag.p, h->d_prm.p);
     return (int)cudaGetLastError();
 }
 
@@ -904,21 +938,29 @@ static int enqueue_try_begin(islam_pvgo* h, cudaStream_t s) {
 }
 
 // after the all-reduce of the shared panels (multi-GPU) / directly (single GPU): finish the solve, evaluate the trial
-static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
+static int enqueue_try_mid_a(islam_pvgo* h, cudaStream_t s) {
+    if (h->opts.n_parts == 1) return 0;
+    k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
+    int rc = launch_factor_shared(h, s, 0.0, 2);
+    if (!rc && h->root_dist()) rc = launch_root_finish(h, s);
+    return rc;
+}
+static int enqueue_try_mid_b(islam_pvgo* h, cudaStream_t s) {
     const int np_ = h->n_blocks();
-    int rc = 0;
-    if (h->opts.n_parts > 1) {
-        k_begin_step_b<<<1, 32, 0, s>>>(h->st.p, lin_sum_ptr(h));
-        rc = launch_factor_shared(h, s, 0.0, 2);
-        if (rc) return rc;
-    }
-    rc = launch_backsolve(h, s, 0);
+    int rc = launch_backsolve(h, s, 0);
     if (rc) return rc;
     rc = launch_trial(h, s);
     if (rc) return rc;
     if (h->opts.n_parts > 1 && !h->p2p)
         k_reduce2<<<1, 256, 0, s>>>(h->st.p, h->trial_part.p, np_, trial_sum_ptr(h), 0);   // then all-reduced by the caller
     return (int)cudaGetLastError();
+}
+// With a distributed dense root the caller drives the block columns between the two halves (islam_pvgo_root_panel,
+// a broadcast of the panel from its owner, islam_pvgo_root_update); otherwise both halves run back to back.
+static int enqueue_try_mid(islam_pvgo* h, cudaStream_t s) {
+    int rc = enqueue_try_mid_a(h, s);
+    if (rc || h->root_dist()) return rc;
+    return enqueue_try_mid_b(h, s);
 }
 
 static int enqueue_try_end(islam_pvgo* h, cudaStream_t s) {
@@ -980,6 +1022,28 @@ extern "C" int islam_pvgo_lm_try_begin(islam_pvgo* h, void* stream) {
 extern "C" int islam_pvgo_lm_try_mid(islam_pvgo* h, void* stream) {
     if (!h) return -1;
     return enqueue_try_mid(h, (cudaStream_t)stream);
+}
+extern "C" int islam_pvgo_lm_try_mid2(islam_pvgo* h, void* stream) {
+    if (!h || !h->root_dist()) return -1;
+    return enqueue_try_mid_b(h, (cudaStream_t)stream);
+}
+extern "C" int islam_pvgo_root_buffers(islam_pvgo* h, double** R, int64_t* n, int64_t* ld, double** diag, int32_t* block) {
+    if (!h || !R || !n || !ld || !diag || !block) return -1;
+    if (!h->root_dist()) { *R = nullptr; *diag = nullptr; *n = 0; *ld = 0; *block = DR_NB; return 0; }
+    *R = h->rv.R; *n = h->rv.n; *ld = h->rv.ld; *diag = h->root_diag.p; *block = DR_NB;
+    return 0;
+}
+extern "C" int islam_pvgo_root_owner(const islam_pvgo* h, int64_t k0) {
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n) return -1;
+    return (int)((k0 / SY_T) % h->opts.n_parts);
+}
+extern "C" int islam_pvgo_root_panel(islam_pvgo* h, int64_t k0, void* stream) {
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % DR_NB) return -1;
+    return launch_root_panel(h, (cudaStream_t)stream, (int)k0, 0);
+}
+extern "C" int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream) {
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % DR_NB) return -1;
+    return launch_root_update(h, (cudaStream_t)stream, (int)k0, 0);
 }
 extern "C" int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream) {
     if (!h) return -1;

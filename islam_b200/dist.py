@@ -46,6 +46,16 @@ class ShardedPVGO:
         self.shared = _wrap(p.value, n.value, self.s.device)
         _lib.check(L.islam_pvgo_sums_buffer(h, C.byref(p), C.byref(n)), 'islam_pvgo_sums_buffer')
         self.sums = _wrap(p.value, n.value, self.s.device)
+        # dense loop-closure root (BASELINE config 4): factored by all ranks together, see lm_try
+        rp, rn, rld, dp, blk = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_void_p(), C.c_int32()
+        _lib.check(L.islam_pvgo_root_buffers(h, C.byref(rp), C.byref(rn), C.byref(rld), C.byref(dp), C.byref(blk)),
+                   'islam_pvgo_root_buffers')
+        self.root_n, self.root_ld, self.root_block = rn.value, rld.value, blk.value
+        if self.root_n:
+            self.root_R = _wrap(rp.value, self.root_n * self.root_ld, self.s.device)
+            self.root_diag = _wrap(dp.value, self.root_n, self.s.device)
+            self._root_owner = [L.islam_pvgo_root_owner(h, k0) for k0 in range(0, self.root_n, self.root_block)]
+            self._root_src = [o if group is None else dist.get_global_rank(group, o) for o in self._root_owner]
         parts = np.zeros(3 * N, np.int32)
         _lib.check(L.islam_pvgo_var_parts(h, parts.ctypes.data), 'islam_pvgo_var_parts')
         self.var_parts = parts = parts.reshape(N, 3)            # [tau, phi, v] of every pose
@@ -86,13 +96,37 @@ class ShardedPVGO:
             dist.all_reduce(c, group=self.group)
             t.copy_(c)
 
+    def _bcast(self, t, src):
+        if self._nccl:
+            dist.broadcast(t, src, group=self.group)
+        else:                                   # gloo: stage through the host
+            c = t.cpu()
+            dist.broadcast(c, src, group=self.group)
+            t.copy_(c)
+
+    def _root_factor(self, st):
+        """Dense root, 1-D block-column-cyclic right-looking Cholesky (include/islam_pvgo.h): per block column the owner
+        factors the diagonal block and the panel below, broadcasts it (NCCL over NVSwitch), and every rank updates its own
+        tile columns of the trailing matrix with it (the n^3/3 of the work, split G ways)."""
+        s, n, ld, nb = self.s, self.root_n, self.root_ld, self.root_block
+        for b, k0 in enumerate(range(0, n, nb)):
+            _lib.check(s.L.islam_pvgo_root_panel(s._h, k0, st), 'islam_pvgo_root_panel')
+            self._bcast(self.root_R[k0 * ld:min(k0 + nb, n) * ld], self._root_src[b])
+            _lib.check(s.L.islam_pvgo_root_update(s._h, k0, st), 'islam_pvgo_root_update')
+
     def lm_try(self):
         s = self.s
         st = C.c_void_p(s.stream.cuda_stream)
         with torch.cuda.stream(s.stream):
             _lib.check(s.L.islam_pvgo_lm_try_begin(s._h, st), 'islam_pvgo_lm_try_begin')
             self._allreduce(self.shared)
+            if self.root_n:
+                self._allreduce(self.root_R)
+                self._allreduce(self.root_diag)
             _lib.check(s.L.islam_pvgo_lm_try_mid(s._h, st), 'islam_pvgo_lm_try_mid')
+            if self.root_n:
+                self._root_factor(st)
+                _lib.check(s.L.islam_pvgo_lm_try_mid2(s._h, st), 'islam_pvgo_lm_try_mid2')
             if self.exchange == 'nccl':
                 self._allreduce(self.sums)
             _lib.check(s.L.islam_pvgo_lm_try_end(s._h, st), 'islam_pvgo_lm_try_end')
@@ -127,8 +161,10 @@ class ShardedPVGO:
         s._enter()
         if budget is None:                      # same policy as islam_pvgo_lm_run
             budget = min(s.params.max_steps + 2, 4) if s.params.use_scheduler else s.params.max_steps + 2
-        g = self._graph_try() if self.use_graph else None
-        for _ in range(64):
+        if self.root_n:                         # a surplus try would still broadcast the whole root: check after every try
+            budget = 1
+        g = self._graph_try() if self.use_graph and not self.root_n else None
+        for _ in range(64 * (4 if self.root_n else 1)):
             for _ in range(budget):
                 if g is not None:
                     with torch.cuda.stream(s.stream):
@@ -138,7 +174,7 @@ class ShardedPVGO:
             st = s.lm_state()
             if not st.continual:
                 return st
-            budget = 4
+            budget = 1 if self.root_n else 4
         return st
 
     # opt-in (ISLAM_SHARDED_GRAPH=1): replaying the captured try measured 2 271 LM it/s against 2 254 eager on two B200 (the

@@ -14,6 +14,11 @@ from islam_b200 import synth
 from oracle import pvgo_oracle as po
 
 
+_GRAPHS = {'band8': lambda: synth.config2(N=260, band=8), 'lc': lambda: synth.config4(N=300, n_lc=5, min_gap=40),
+           # enough closures for the DENSE root (csrc/dense_root.cuh), which all ranks then factor together
+           'lcdense': lambda: synth.config4(N=420, n_lc=40, min_gap=40)}
+
+
 def _partial_system(g, plan, rank):
     """H, g assembled from the factors `rank` owns only (ownership rule of csrc/pvgo.cu)."""
     lm = po.SparseLM(g, np.float64)
@@ -51,7 +56,7 @@ def _partial_system(g, plan, rank):
 def _worker(rank, world, port, name, out_dir):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    g = {'band8': lambda: synth.config2(N=260, band=8), 'lc': lambda: synth.config4(N=300, n_lc=5, min_gap=40)}[name]()
+    g = _GRAPHS[name]()
     plan = mf_emul.get_plan(g.N, g.links, n_parts=world)
     H, gg = _partial_system(g, plan, rank)
     Hd, Ho = mf_emul.blocks_from_dense(H, plan, g.N)
@@ -72,14 +77,16 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,name', [(2, 'band8'), (4, 'band8'), (8, 'band8'), (2, 'lc')])
+@pytest.mark.parametrize('world,name', [(2, 'band8'), (4, 'band8'), (8, 'band8'), (2, 'lc'), (2, 'lcdense'), (4, 'lcdense')])
 def test_sharded_scheme_reproduces_dense_solve(world, name, tmp_path):
     port = 29600 + world * 7 + len(name)
     mp.spawn(_worker, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
     r = np.load(tmp_path / 'r.npz')
     H, gg, D = r['H'], r['g'], r['D']
     # the per-rank partial systems sum to the oracle's full system
-    g = {'band8': lambda: synth.config2(N=260, band=8), 'lc': lambda: synth.config4(N=300, n_lc=5, min_gap=40)}[name]()
+    g = _GRAPHS[name]()
+    if name == 'lcdense':
+        assert mf_emul.get_plan(g.N, g.links, n_parts=world)['dense_root'] >= 0
     lm = po.SparseLM(g, np.float64)
     Href, gref, _, _ = lm.assemble(lm._res())
     assert np.abs(H - Href.toarray()).max() < 1e-9 * np.abs(H).max()

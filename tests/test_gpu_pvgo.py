@@ -136,24 +136,49 @@ def test_window_with_scheduler_matches_oracle():
     assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= 1e-5
 
 
-def _mg_worker(rank, world, port, out, exchange):
+_MG_GRAPHS = {'band8': (lambda: synth.config2(N=600, band=8), 5),
+              # 70 loop closures => a dense root of ~140 poses (~850 unknowns, 7 tile columns), csrc/dense_root.cuh
+              'lcdense': (lambda: synth.config4(N=2500, n_lc=70, min_gap=100), 4)}
+
+
+def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False):
     import os
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dev = torch.device('cuda', rank)
-    dist.init_process_group('nccl', device_id=dev)
+    dev = torch.device('cuda', 0 if one_gpu else rank)
+    torch.cuda.set_device(dev)
+    if one_gpu:                                  # all ranks on ONE device: NCCL refuses that, gloo stages through the host
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    else:
+        dist.init_process_group('nccl', device_id=dev)
     from islam_b200.dist import ShardedPVGO
-    g = synth.config2(N=600, band=8)
+    mk, steps = _MG_GRAPHS[name]
+    g = mk()
     sh = ShardedPVGO(g.N, g.links, dev, exchange=exchange)
     sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
     sh.set_state(g.init_nodes, g.init_vels)
-    sh.lm_reset(radius=g.radius, max_steps=5, use_scheduler=0)
+    sh.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
     st = sh.lm_run()
     n, v = sh.get_state()
     if rank == 0:
-        torch.save(dict(nodes=n.cpu(), vels=v.cpu(), loss=st.loss, steps=st.steps_done), out)
+        torch.save(dict(nodes=n.cpu(), vels=v.cpu(), loss=st.loss, steps=st.steps_done, rejects=st.reject_count, info=st.info,
+                        root_n=sh.root_n, n_shared=sh.s.dims.n_shared_fronts), out)
     dist.destroy_process_group()
+
+
+def _check_sharded(out, name, loss_rtol=1e-9):
+    r = torch.load(out)
+    mk, steps = _MG_GRAPHS[name]
+    g = mk()
+    s = _solver(g)
+    s.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
+    st = s.lm_run()
+    n1, v1 = s.get_state()
+    assert r['info'] == 0 and r['steps'] == steps and abs(r['loss'] - st.loss) <= loss_rtol * st.loss
+    assert (r['nodes'] - n1.cpu()).abs().max().item() <= 1e-6
+    ref = po.SparseLM(g, np.float64, solver='splu' if name == 'lcdense' else 'auto').run(steps=steps)
+    assert po.rel_pose_error(r['nodes'].numpy(), ref.nodes)['rel'] <= 1e-5
+    return r
 
 
 @pytest.mark.parametrize('world,exchange', [(2, 'p2p'), (2, 'nccl'), (4, 'p2p')])
@@ -166,16 +191,32 @@ def test_sharded_lm_matches_single_gpu_and_oracle(world, exchange, tmp_path):
     import torch.multiprocessing as mp
     out = str(tmp_path / 'mg.pt')
     mp.spawn(_mg_worker, args=(world, 29533 + world + (7 if exchange == 'nccl' else 0), out, exchange), nprocs=world, join=True)
-    r = torch.load(out)
-    g = synth.config2(N=600, band=8)
-    s = _solver(g)
-    s.lm_reset(radius=g.radius, max_steps=5, use_scheduler=0)
-    st = s.lm_run()
-    n1, v1 = s.get_state()
-    assert r['steps'] == 5 and abs(r['loss'] - st.loss) <= 1e-9 * st.loss
-    assert (r['nodes'] - n1.cpu()).abs().max().item() <= 1e-6
-    ref = po.SparseLM(g, np.float64).run(steps=5)
-    assert po.rel_pose_error(r['nodes'].numpy(), ref.nodes)['rel'] <= 1e-5
+    _check_sharded(out, 'band8')
+
+
+@pytest.mark.parametrize('world,name', [(2, 'band8'), (2, 'lcdense'), (4, 'lcdense')])
+def test_sharded_ranks_on_one_gpu(world, name, tmp_path):
+    """The N>1 path on a ONE-GPU box: `world` processes share cuda:0 and exchange through gloo (host-staged), so the
+    sharded kernels — stage 1 / 2 of the separator fronts, the partial root, the block-column-cyclic dense-root Cholesky with
+    its panel broadcasts (csrc/dense_root.cuh, include/islam_pvgo.h) — run wherever the GPU tests run."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'mg1.pt')
+    mp.spawn(_mg_worker, args=(world, 29571 + world + len(name), out, 'nccl', name, True), nprocs=world, join=True)
+    r = _check_sharded(out, name, loss_rtol=1e-8)
+    assert (r['root_n'] > 0) == (name == 'lcdense')
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_dense_root_over_nccl(world, tmp_path):
+    """Config-4 structure on `world` GPUs: all-reduce of the partial root, then the distributed dense-root factorisation
+    (NCCL broadcast of every factored block column from its owner)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'mgd.pt')
+    mp.spawn(_mg_worker, args=(world, 29611 + world, out, 'p2p', 'lcdense'), nprocs=world, join=True)
+    r = _check_sharded(out, 'lcdense', loss_rtol=1e-8)
+    assert r['root_n'] > 0
 
 
 def test_config3_kitti_length_chain_with_gpu_preintegration():
