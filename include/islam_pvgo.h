@@ -163,9 +163,10 @@ int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream);
  *      clamp is not linear, travels apart)
  *   try_mid   : shared fronts, then the root's clamped + damped diagonal; returns BEFORE the root is factored
  *   for k0 = 0, block, 2 block ... < n:
- *       islam_pvgo_root_panel(k0)                       (a no-op except on islam_pvgo_root_owner(k0))
+ *       islam_pvgo_root_panel(k0)                       (factors the block's columns; a no-op except on
+ *                                                        islam_pvgo_root_owner(k0))
  *       -> broadcast of R[k0 * ld, (k0 + min(block, n - k0)) * ld) from that owner (the factored block column)
- *       islam_pvgo_root_update(k0)                      (trailing update of this rank's tile columns)
+ *       islam_pvgo_root_update(k0)                      (trailing update of this rank's tile columns; block = 128)
  *   try_mid2  : root back-substitution (replicated), the window's back-substitution, retract, trial residuals
  *   try_end   : as above.
  * islam_pvgo_root_buffers returns n == 0 when the graph has no dense root or n_parts == 1 (then try_mid does it all and
@@ -174,6 +175,10 @@ int islam_pvgo_root_buffers(islam_pvgo* h, double** R, int64_t* n, int64_t* ld, 
 int islam_pvgo_root_owner(const islam_pvgo* h, int64_t k0);
 int islam_pvgo_root_panel(islam_pvgo* h, int64_t k0, void* stream);
 int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream);
+/* look-ahead: root_update split in two — which = 1: only the NEXT block's tile column (work for islam_pvgo_root_owner(k0 +
+ * block) alone), which = 2: everything right of it.  After part 1 the next block can be factored and broadcast on a second
+ * stream while part 2 of this block still runs (islam_b200/dist.py). */
+int islam_pvgo_root_update_part(islam_pvgo* h, int64_t k0, int32_t which, void* stream);
 int islam_pvgo_lm_try_mid2(islam_pvgo* h, void* stream);
 /* peer mailboxes: every rank exports the IPC handle of its mailbox (64 bytes), the caller all-gathers them (rank order)
  * and hands the table to every rank.  LM state info = 2 reports a peer that never answered (2 s timeout). */

@@ -534,14 +534,15 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         for (int k = q.f_child_off[fr]; k < q.f_child_off[fr + 1]; ++k) kids.push_back(k);
         cudaError_t e1 = h->d_root_vars.upload(rvars);
         if (e1 == cudaSuccess) e1 = h->d_root_children.upload(kids);
-        if (e1 == cudaSuccess) e1 = h->root_x.alloc(3 * (size_t)K + 1);
+        if (e1 == cudaSuccess) e1 = h->root_x.alloc(2 * (3 * (size_t)K + 1));             // x and the running right-hand side t
         if (e1 == cudaSuccess && opts.n_parts > 1) e1 = h->root_diag.alloc(3 * (size_t)K);      // multi-GPU: summed apart, then clamped
         if (e1 != cudaSuccess) { delete h; return (int)e1; }
         RootView& rv = h->rv;
-        rv.R = h->Lbuf.p + q.f_Loff[fr]; rv.n = 3 * K; rv.ld = 3 * K + 1; rv.K = K; rv.front = fr;
+        rv.R = h->Lbuf.p + q.f_Loff[fr]; rv.n = 3 * K; rv.ld = (3 * K + 2) & ~1; rv.K = K; rv.front = fr;      // ld even (symbolic3.cpp)
         rv.vars = h->d_root_vars.p; rv.children = h->d_root_children.p; rv.nchildren = (int)kids.size();
         h->has_root = true;
-        cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128)));
+        cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM);
+        cudaFuncSetAttribute(k_root_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PO_SMEM);
         cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
     }
     // LM state
@@ -749,25 +750,44 @@ static int launch_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
 }
 
 // ---- dense root: tiled right-looking Cholesky of the loop-closure Schur complement, then its back-substitution ----------
-// one block column of the right-looking factorisation: diagonal block + the panel below (the tile column's owner only) ...
-static int launch_root_panel(islam_pvgo* h, cudaStream_t s, int k0, int force) {
-    const RootView& rv = h->rv;
-    const int G = h->opts.n_parts, nbk = std::min(DR_NB, rv.n - k0);
-    if ((k0 / SY_T) % G != h->opts.part) return 0;
-    k_root_potrf<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, force, &h->st.p->chol_fail);
-    const int below = rv.n + 1 - (k0 + nbk);                      // rows below, including the rhs row
-    if (below > 0)
-        k_root_trsm<<<(below + 127) / 128, 128, sizeof(double) * (DR_NB * (DR_NB + 1) + DR_NB * 128), s>>>(h->st.p, rv, k0, nbk, force);
-    return (int)cudaGetLastError();
-}
-// ... and the trailing update with it, on this rank's tile columns
-static int launch_root_update(islam_pvgo* h, cudaStream_t s, int k0, int force) {
+// One 128-column block step of the right-looking factorisation (dense_root.cuh), k0 a multiple of SY_T.
+// root_panel (the tile column's owner only): the block's two 64-column panels — diagonal block + triangular solve of the
+// rows below — with a narrow update of the second panel's own columns in between ...
+static int launch_root_potrf_trsm(islam_pvgo* h, cudaStream_t s, int k0, int force) {
     const RootView& rv = h->rv;
     const int nbk = std::min(DR_NB, rv.n - k0);
-    if (k0 + nbk >= rv.n) return 0;
-    const long long ntiles = root_syrk_tiles(rv.n, k0 + nbk, h->opts.n_parts, h->opts.part, nullptr, nullptr);
-    if (ntiles > 0) k_root_syrk<<<(unsigned)ntiles, 256, SY_SMEM, s>>>(h->st.p, rv, k0, nbk, force, h->opts.n_parts, h->opts.part);
+    k_root_potrf<<<1, 256, PO_SMEM, s>>>(h->st.p, rv, k0, nbk, force, &h->st.p->chol_fail);
+    const int below = rv.n + 1 - (k0 + nbk);                      // rows below, including the rhs row
+    if (below > 0)
+        k_root_trsm<<<(below + 127) / 128, 128, TR_SMEM, s>>>(h->st.p, rv, k0, nbk, force);
     return (int)cudaGetLastError();
+}
+static int launch_root_syrk(islam_pvgo* h, cudaStream_t s, int k0, int nk, int base, int c_hi, int force) {
+    const RootView& rv = h->rv;
+    if (base >= rv.n) return 0;
+    const long long ntiles = root_syrk_tiles(rv.n, base, c_hi, h->opts.n_parts, h->opts.part, nullptr, nullptr, nullptr);
+    if (ntiles > 0)
+        k_root_syrk<<<(unsigned)(2 * ntiles), SY_THREADS, SY_SMEM, s>>>(h->st.p, rv, k0, nk, base, c_hi, force, h->opts.n_parts, h->opts.part);
+    return (int)cudaGetLastError();
+}
+static int launch_root_panel(islam_pvgo* h, cudaStream_t s, int k0, int force) {
+    const RootView& rv = h->rv;
+    if ((k0 / SY_T) % h->opts.n_parts != h->opts.part) return 0;
+    int rc = launch_root_potrf_trsm(h, s, k0, force);
+    if (rc || k0 + DR_NB >= rv.n) return rc;
+    rc = launch_root_syrk(h, s, k0, DR_NB, k0 + DR_NB, k0 + SY_T, force);      // tile column k0 / SY_T only: this rank's
+    if (!rc) rc = launch_root_potrf_trsm(h, s, k0 + DR_NB, force);
+    return rc;
+}
+// ... root_update: the trailing update with all (up to) 128 columns of the block, on this rank's tile columns
+// which: 0 = everything, 1 = only the NEXT block's tile column (its owner can then factor it while the others are still
+// updating: look-ahead), 2 = everything right of that column
+static int launch_root_update(islam_pvgo* h, cudaStream_t s, int k0, int force, int which = 0) {
+    const RootView& rv = h->rv;
+    const int nk = std::min(SY_T, rv.n - k0);
+    if (which == 1) return launch_root_syrk(h, s, k0, nk, k0 + nk, k0 + nk + SY_T, force);
+    if (which == 2) return launch_root_syrk(h, s, k0, nk, k0 + nk + SY_T, rv.n, force);
+    return launch_root_syrk(h, s, k0, nk, k0 + nk, rv.n, force);
 }
 
 static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
@@ -789,7 +809,7 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
     k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min,
                                                     q.lm_max, (double*)nullptr);
     if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, ROOT_ALL_CHILDREN);
-    for (int k0 = 0; k0 < rv.n; k0 += DR_NB) {
+    for (int k0 = 0; k0 < rv.n; k0 += SY_T) {
         int rc = launch_root_panel(h, s, k0, force);
         if (!rc) rc = launch_root_update(h, s, k0, force);
         if (rc) return rc;
@@ -809,12 +829,16 @@ static int launch_root_finish(islam_pvgo* h, cudaStream_t s) {
 static int launch_root_solve(islam_pvgo* h, cudaStream_t s, int force) {
     if (!h->has_root) return 0;
     const RootView& rv = h->rv;
+    double* x = h->root_x.p;
+    double* t = h->root_x.p + rv.n + 1;
+    k_root_back_init<<<(rv.n + 255) / 256, 256, 0, s>>>(h->st.p, rv, t, force);
     int nblk = (rv.n + DR_NB - 1) / DR_NB;
     for (int b = nblk - 1; b >= 0; --b) {
         int k0 = b * DR_NB, nbk = std::min(DR_NB, rv.n - k0);
-        k_root_back<<<1, 256, 0, s>>>(h->st.p, rv, k0, nbk, h->root_x.p, force);
+        int grid = std::max(1, std::min(h->n_sm, (k0 + 31) / 32));          // >= 4 columns per warp
+        k_root_back<<<grid, RB_THREADS, 0, s>>>(h->st.p, rv, k0, nbk, x, t, force);
     }
-    k_root_scatter<<<(rv.n + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->root_x.p, h->D.p, force);
+    k_root_scatter<<<(rv.n + 127) / 128, 128, 0, s>>>(h->st.p, rv, x, h->D.p, force);
     return (int)cudaGetLastError();
 }
 
@@ -1029,8 +1053,8 @@ extern "C" int islam_pvgo_lm_try_mid2(islam_pvgo* h, void* stream) {
 }
 extern "C" int islam_pvgo_root_buffers(islam_pvgo* h, double** R, int64_t* n, int64_t* ld, double** diag, int32_t* block) {
     if (!h || !R || !n || !ld || !diag || !block) return -1;
-    if (!h->root_dist()) { *R = nullptr; *diag = nullptr; *n = 0; *ld = 0; *block = DR_NB; return 0; }
-    *R = h->rv.R; *n = h->rv.n; *ld = h->rv.ld; *diag = h->root_diag.p; *block = DR_NB;
+    if (!h->root_dist()) { *R = nullptr; *diag = nullptr; *n = 0; *ld = 0; *block = SY_T; return 0; }
+    *R = h->rv.R; *n = h->rv.n; *ld = h->rv.ld; *diag = h->root_diag.p; *block = SY_T;
     return 0;
 }
 extern "C" int islam_pvgo_root_owner(const islam_pvgo* h, int64_t k0) {
@@ -1038,12 +1062,16 @@ extern "C" int islam_pvgo_root_owner(const islam_pvgo* h, int64_t k0) {
     return (int)((k0 / SY_T) % h->opts.n_parts);
 }
 extern "C" int islam_pvgo_root_panel(islam_pvgo* h, int64_t k0, void* stream) {
-    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % DR_NB) return -1;
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % SY_T) return -1;
     return launch_root_panel(h, (cudaStream_t)stream, (int)k0, 0);
 }
 extern "C" int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream) {
-    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % DR_NB) return -1;
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % SY_T) return -1;
     return launch_root_update(h, (cudaStream_t)stream, (int)k0, 0);
+}
+extern "C" int islam_pvgo_root_update_part(islam_pvgo* h, int64_t k0, int32_t which, void* stream) {
+    if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % SY_T || which < 1 || which > 2) return -1;
+    return launch_root_update(h, (cudaStream_t)stream, (int)k0, 0, which);
 }
 extern "C" int islam_pvgo_lm_try_end(islam_pvgo* h, void* stream) {
     if (!h) return -1;

@@ -214,7 +214,9 @@ int build_plan3(const Plan& base, const int64_t* links, const SymbolicOpts& opts
         p.f_vars.insert(p.f_vars.end(), npad - np, -1);
         p.f_vars.insert(p.f_vars.end(), boundary[f].begin(), boundary[f].end());
         const long long cols = 3LL * npad, ub = 3LL * nb + 1, rows = cols + ub;
-        p.f_Loff[f] = p.L_doubles; p.L_doubles += (rows * cols + 1) & ~1LL;     // even: every panel starts 16-byte aligned (TMA bulk copies)
+        // even: every panel starts 16-byte aligned (TMA bulk copies); the dense root's leading dimension is even too
+        // (dense_root.cuh: its operand panels are fetched by bulk copies of whole column segments)
+        p.f_Loff[f] = p.L_doubles; p.L_doubles += (((f == p.dense_root) ? ((rows + 1) & ~1LL) : rows) * cols + 1) & ~1LL;
         const long long ube = (ub + 1) & ~1LL;                     // paired-column layout of solver3.cuh (f3_ulen)
         p.f_Uoff[f] = p.U_doubles; p.U_doubles += ube * (ube / 2 + 1);
         p.f_Ioff[f] = p.I_doubles; p.I_doubles += (f == p.dense_root) ? 0 : 81LL * (npad / 3);

@@ -105,14 +105,42 @@ class ShardedPVGO:
             t.copy_(c)
 
     def _root_factor(self, st):
-        """Dense root, 1-D block-column-cyclic right-looking Cholesky (include/islam_pvgo.h): per block column the owner
-        factors the diagonal block and the panel below, broadcasts it (NCCL over NVSwitch), and every rank updates its own
-        tile columns of the trailing matrix with it (the n^3/3 of the work, split G ways)."""
+        """Dense root, 1-D block-column-cyclic right-looking Cholesky (include/islam_pvgo.h): per 128-column block the owner
+        factors it, broadcasts it (NCCL over NVSwitch), and every rank updates its own tile columns of the trailing matrix
+        with it (the n^3/3 of the work, split G ways).  Look-ahead: the NEXT block's tile column is updated first, so that
+        its owner factors it and the broadcast travels on a second stream while all ranks are still busy with the rest of
+        this block's update — the chain of panel factorisations and broadcasts leaves the critical path."""
         s, n, ld, nb = self.s, self.root_n, self.root_ld, self.root_block
-        for b, k0 in enumerate(range(0, n, nb)):
-            _lib.check(s.L.islam_pvgo_root_panel(s._h, k0, st), 'islam_pvgo_root_panel')
-            self._bcast(self.root_R[k0 * ld:min(k0 + nb, n) * ld], self._root_src[b])
-            _lib.check(s.L.islam_pvgo_root_update(s._h, k0, st), 'islam_pvgo_root_update')
+        L, h = s.L, s._h
+        main = s.stream
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=s.device)
+            self._root_ev = [torch.cuda.Event() for _ in range(2)]
+        side, side_p = self._side, C.c_void_p(self._side.cuda_stream)
+        blocks = list(range(0, n, nb))
+        _lib.check(L.islam_pvgo_root_panel(h, 0, st), 'islam_pvgo_root_panel')
+        self._bcast(self.root_R[0:min(nb, n) * ld], self._root_src[0])
+        for b, k0 in enumerate(blocks):
+            k1 = k0 + nb
+            if not self.lookahead or k1 >= n:
+                _lib.check(L.islam_pvgo_root_update(h, k0, st), 'islam_pvgo_root_update')
+                if k1 < n:
+                    _lib.check(L.islam_pvgo_root_panel(h, k1, st), 'islam_pvgo_root_panel')
+                    self._bcast(self.root_R[k1 * ld:min(k1 + nb, n) * ld], self._root_src[b + 1])
+                continue
+            _lib.check(L.islam_pvgo_root_update_part(h, k0, 1, st), 'islam_pvgo_root_update_part')
+            ready, done = self._root_ev
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                _lib.check(L.islam_pvgo_root_panel(h, k1, side_p), 'islam_pvgo_root_panel')
+                self._bcast(self.root_R[k1 * ld:min(k1 + nb, n) * ld], self._root_src[b + 1])
+                done.record(side)
+            _lib.check(L.islam_pvgo_root_update_part(h, k0, 2, st), 'islam_pvgo_root_update_part')
+            main.wait_event(done)
+
+    _side = None
+    lookahead = os.environ.get('ISLAM_ROOT_LOOKAHEAD', '1') != '0'
 
     def lm_try(self):
         s = self.s
