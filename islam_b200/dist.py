@@ -114,7 +114,10 @@ class ShardedPVGO:
         L, h = s.L, s._h
         main = s.stream
         if self._side is None:
-            self._side = torch.cuda.Stream(device=s.device)
+            # high priority: the panel kernels and the broadcast must get SMs while the wide update of the previous block
+            # still has thousands of CTAs queued, or the look-ahead only starts when that update drains.  For the same
+            # reason launch with TORCH_NCCL_HIGH_PRIORITY=1 (torch then creates its NCCL streams with high priority).
+            self._side = torch.cuda.Stream(device=s.device, priority=-1)
             self._root_ev = [torch.cuda.Event() for _ in range(2)]
         side, side_p = self._side, C.c_void_p(self._side.cuda_stream)
         blocks = list(range(0, n, nb))

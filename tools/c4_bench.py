@@ -6,6 +6,7 @@ stream; the multi-GPU line is the max over ranks.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tools/c4_bench.py
 """
 import argparse, ctypes as C, os, sys, time
+os.environ.setdefault('TORCH_NCCL_HIGH_PRIORITY', '1')      # see islam_b200/dist.py: look-ahead broadcasts
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from islam_b200 import synth, _lib
