@@ -303,7 +303,8 @@ constexpr int SY_KC = 32;                       // k chunk
 constexpr int SY_LDA = SY_T + 4, SY_LDB = SY_TN + 4;      // row strides = 4 mod 16 doubles: conflict-free fragment loads
 constexpr int SY_STAGE = SY_KC * (SY_LDA + SY_LDB);       // doubles per pipeline stage
 constexpr size_t SY_SMEM = sizeof(double) * 2 * SY_STAGE;
-constexpr int SY_THREADS = 128;
+constexpr int SY_WN = 32;                       // warp tile width: 32 -> 8 warps per CTA, 16 per SM (64 -> 4 / 8)
+constexpr int SY_THREADS = 128 * (SY_TN / SY_WN);
 
 // this rank's 128 x 128 tiles (each one = two CTAs) of the update of columns [base, c_hi)
 __host__ __device__ inline long long root_syrk_tiles(int n, int base, int c_hi, int G, int rank, int* T_out, int* j0_out,
@@ -334,7 +335,8 @@ __device__ __forceinline__ void tma_copy_1d(void* dst_smem, const void* src_gmem
 // copies per chunk issued by ONE thread and counted on the stage's mbarrier.  (The 8-byte cp.async version spent 87 % of its
 // issue slots on copy instructions and their addresses and stalled on the LSU queues: ncu r02_root_syrk_*.)  nk is 64 or
 // 128 in every launch (the ragged last block of the matrix has nothing to update), so chunks are always complete.
-__global__ void __launch_bounds__(SY_THREADS, 2)
+template <int WN>                                   // warp tile 32 x WN; (SY_TN / WN) * 4 warps per CTA
+__global__ void __launch_bounds__(128 * (SY_TN / WN), 2)
 k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int base, int c_hi, int force, int G, int rank) {
     if (!force && !st->active) return;
     extern __shared__ __align__(16) double sm_syrk[];
@@ -350,8 +352,10 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
     const int cmax = c_hi < rv.n ? c_hi : rv.n;             // columns [base, cmax)
     if (c0 + SY_TN <= base || c0 >= cmax || r0 + SY_T <= c0) return;       // nothing of this tile is in the update
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wr = 32 * w;                                  // this warp's 32 x 64 piece of the tile
-    const bool idle = r0 + wr + 32 <= c0 || r0 + wr + 32 <= base;          // entirely above the diagonal / above `base`
+    constexpr int NJ = WN / 8;
+    const int wr = 32 * (w & 3), wc = WN * (w >> 2);        // this warp's 32 x WN piece of the tile
+    // entirely above the diagonal / above or left of `base`
+    const bool idle = r0 + wr + 32 <= c0 + wc || r0 + wr + 32 <= base || c0 + wc + WN <= base;
     const int lk = lane & 3, lm = lane >> 2;
     const int nchunk = nk / SY_KC;
     const int rowsA = rv.ld - r0 < SY_T ? rv.ld - r0 : SY_T, rowsB = rv.ld - c0 < SY_TN ? rv.ld - c0 : SY_TN;      // even
@@ -375,13 +379,13 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
     // the accumulators start as the C tile itself (its loads overlap the panel copies) and the A fragments are negated:
     // D = (-A) B + C, so the result is stored without a dependent read-modify-write at the end
     const bool interior = c0 >= base && c0 + SY_TN <= cmax && r0 >= c0 + SY_TN - 1 && r0 + SY_T <= rv.n + 1;
-    double acc[4][8][2];
-    double* Cw = rv.R + (size_t)(r0 + wr + lm) + (size_t)(c0 + 2 * lk) * rv.ld;       // this lane's first element
+    double acc[4][NJ][2];
+    double* Cw = rv.R + (size_t)(r0 + wr + lm) + (size_t)(c0 + wc + 2 * lk) * rv.ld;       // this lane's first element
     if (interior) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) acc[i][j][e] = Cw[8 * i + (size_t)(8 * j + e) * rv.ld];
     } else {
@@ -389,10 +393,10 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
         for (int i = 0; i < 4; ++i) {
             const int r = r0 + wr + 8 * i + lm;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int c = c0 + 8 * j + 2 * lk + e;
+                    const int c = c0 + wc + 8 * j + 2 * lk + e;
                     acc[i][j][e] = (!idle && r <= rv.n && c < cmax && r >= c && c >= base) ? Cw[8 * i + (size_t)(8 * j + e) * rv.ld] : 0.0;
                 }
         }
@@ -406,16 +410,16 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
 #pragma unroll 2
             for (int k4 = 0; k4 < SY_KC; k4 += 4) {
                 const double* ap = As + (k4 + lk) * SY_LDA + wr + lm;
-                const double* bp = Bs + (k4 + lk) * SY_LDB + lm;
-                double a[4], b[8];
+                const double* bp = Bs + (k4 + lk) * SY_LDB + wc + lm;
+                double a[4], b[NJ];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[i] = -ap[8 * i];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = bp[8 * j];
+                for (int j = 0; j < NJ; ++j) b[j] = bp[8 * j];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
         __syncthreads();                                    // everybody is done with this stage: refill it
@@ -426,7 +430,7 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) Cw[8 * i + (size_t)(8 * j + e) * rv.ld] = acc[i][j][e];
         return;
@@ -436,10 +440,10 @@ k_root_syrk(const LMState* __restrict__ st, RootView rv, int k0, int nk, int bas
         const int r = r0 + wr + 8 * i + lm;
         if (r > rv.n) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = c0 + 8 * j + 2 * lk + e;
+                const int c = c0 + wc + 8 * j + 2 * lk + e;
                 if (c < cmax && r >= c && c >= base) Cw[8 * i + (size_t)(8 * j + e) * rv.ld] = acc[i][j][e];
             }
     }

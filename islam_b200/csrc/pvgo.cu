@@ -543,7 +543,7 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         h->has_root = true;
         cudaFuncSetAttribute(k_root_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM);
         cudaFuncSetAttribute(k_root_potrf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PO_SMEM);
-        cudaFuncSetAttribute(k_root_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
+        cudaFuncSetAttribute(k_root_syrk<SY_WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
     }
     // LM state
     LMState s;
@@ -767,7 +767,7 @@ static int launch_root_syrk(islam_pvgo* h, cudaStream_t s, int k0, int nk, int b
     if (base >= rv.n) return 0;
     const long long ntiles = root_syrk_tiles(rv.n, base, c_hi, h->opts.n_parts, h->opts.part, nullptr, nullptr, nullptr);
     if (ntiles > 0)
-        k_root_syrk<<<(unsigned)(2 * ntiles), SY_THREADS, SY_SMEM, s>>>(h->st.p, rv, k0, nk, base, c_hi, force, h->opts.n_parts, h->opts.part);
+        k_root_syrk<SY_WN><<<(unsigned)(2 * ntiles), SY_THREADS, SY_SMEM, s>>>(h->st.p, rv, k0, nk, base, c_hi, force, h->opts.n_parts, h->opts.part);
     return (int)cudaGetLastError();
 }
 static int launch_root_panel(islam_pvgo* h, cudaStream_t s, int k0, int force) {
