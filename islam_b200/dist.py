@@ -195,7 +195,8 @@ class ShardedPVGO:
         if self.root_n:                         # a surplus try would still broadcast the whole root: check after every try
             budget = 1
         g = self._graph_try() if self.use_graph and not self.root_n else None
-        for _ in range(64 * (4 if self.root_n else 1)):
+        # worst case: every step burns its 16 rejected tries before it is accepted or abandoned (PyPose's reject=16)
+        for _ in range(2 + 17 * max(1, s.params.max_steps) // (1 if self.root_n else 4)):
             for _ in range(budget):
                 if g is not None:
                     with torch.cuda.stream(s.stream):
@@ -206,7 +207,8 @@ class ShardedPVGO:
             if not st.continual:
                 return st
             budget = 1 if self.root_n else 4
-        return st
+        # as islam_pvgo_lm_run's -9: the loop did not close within its worst-case try budget
+        raise IslamError('ShardedPVGO.lm_run: the LM loop did not finish within its try budget (max_steps too large?)')
 
     # opt-in (ISLAM_SHARDED_GRAPH=1): replaying the captured try measured 2 271 LM it/s against 2 254 eager on two B200 (the
     # critical path is the chain of tree levels, not the launches), and tearing the process group down while a graph that
