@@ -11,6 +11,7 @@
 // configured at pvgo.py:169-180 (lm.cuh: lm_begin_step_b, lm_control), align_to pvgo.py:114-119, vo_loss
 // pvgo.py:67-78.  float32 residuals / Jacobians, float64 normal equations and Cholesky, like everywhere else.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ constexpr int SM_MAX_N = 16;             // poses per window (9 N <= 144 unknown
 constexpr int SM_MAX_E = 128;
 
 struct SmallArgs {
+    int nspec;                           // speculative retry slots that fit shared memory (0 / 1: off)
     int N, E, M, B, bw, span;            // span = max |i - j| over the edges (>= 1: the IMU chain); bw = 9 (span + 1) - 1 scalar sub-diagonals
     const int* links;                    // [E, 2] int32, shared by all windows
     const float *nodes0, *vels0, *Z, *drot, *dtrans, *dvel, *dt;          // batched, window-major
@@ -48,6 +50,175 @@ __host__ __device__ inline size_t small_smem_bytes(int N, int E) {
     size_t d = (size_t)ld * n + 7 * (size_t)n + 16;                          // A, diag0, dinv, g, y, D, diagW (+ slack)
     size_t f = 2 * (size_t)N * 10 + (size_t)E * (7 + 6 + 18) + (size_t)M * (4 + 3 + 3 + 1 + 9 + 9);
     return d * sizeof(double) + (f + 2 * (size_t)E + 8) * sizeof(float);
+}
+
+
+// ---- pieces of one LM try that a single warp can run on its own (the sequential path and the speculative retries share
+// them, so both produce bit-identical numbers) ---------------------------------------------------------------------------
+
+// Block-banded Cholesky with the right-hand side riding along, by ONE warp (scheme of front4.cuh: every lane holds the whole
+// 9 x 9 diagonal block in registers and factors it redundantly, lane l owns row l below the block, the lane after the last
+// row the right-hand side).  W(row, col) = W[col + row * ldw] is the working copy of the strictly lower band (row i of L),
+// diagW the working diagonal, yv the right-hand side; on return W / dinv / yv hold L, 1 / L_jj and the forward-substituted rhs.
+__device__ __forceinline__ bool small_factor_warp(double* __restrict__ W, int ldw, double* __restrict__ diagW,
+                                                  double* __restrict__ yv, double* __restrict__ dinv, int n, int bwn, int lane) {
+    bool ok = true;
+    for (int c0 = 0; c0 < n; c0 += 9) {
+        const int nbelow = min(bwn, n - c0 - 9);
+        const bool is_row = lane < nbelow, is_rhs = lane == nbelow;
+        const int i = c0 + 9 + lane;
+        double D[9][9], isv[9], r[9];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            D[p][p] = diagW[c0 + p];
+#pragma unroll
+            for (int q = 0; q < p; ++q) D[p][q] = W[(c0 + q) + (c0 + p) * ldw];
+        }
+        double* rowp = is_row ? W + c0 + i * ldw : yv + c0;       // this lane's nine entries of the block column
+#pragma unroll
+        for (int q = 0; q < 9; ++q) r[q] = (is_row || is_rhs) ? rowp[q] : 0.0;
+        F4Diag<0>::run(D, isv, ok);
+        f4_row_solve(r, D, isv);
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            dinv[c0 + p] = isv[p];
+#pragma unroll
+            for (int q = 0; q < p; ++q) W[(c0 + q) + (c0 + p) * ldw] = D[p][q];
+        }
+        if (is_row || is_rhs) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) rowp[q] = r[q];
+        }
+        __syncwarp();
+        // trailing update inside the band: W[i][j'] -= sum_q L[i][q] L[j'][q] for the rows j' <= i below the block
+        // (nine rows j' at a time, all accumulators independent: the loads are issued together, not one
+        // dependent load -> fma chain per entry)
+        for (int u0 = 0; u0 < nbelow; u0 += 9) {
+            double s_[9];
+#pragma unroll
+            for (int u = 0; u < 9; ++u) s_[u] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+#pragma unroll
+                for (int u = 0; u < 9; ++u) {
+                    const int uu = u0 + u < nbelow ? u0 + u : u0;
+                    s_[u] = fma(r[q], W[c0 + q + (c0 + 9 + uu) * ldw], s_[u]);       // L[j'][c0 + q], broadcast
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int uu = u0 + u;
+                if (uu >= nbelow) continue;
+                if (is_rhs) yv[c0 + 9 + uu] -= s_[u];
+                else if (is_row && lane == uu) diagW[i] -= s_[u];
+                else if (is_row && lane > uu) W[(c0 + 9 + uu) + i * ldw] -= s_[u];
+            }
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// L^T D = y by one warp (Dv starts as y)
+__device__ __forceinline__ void small_backsolve_warp(const double* __restrict__ W, int ldw, const double* __restrict__ dinv,
+                                                     double* __restrict__ Dv, int n, int bw, int lane) {
+    int offj = (n - 1) * ldw;
+    for (int j = n - 1; j >= 0; --j, offj -= ldw) {
+        const double dj = Dv[j] * dinv[j];
+        __syncwarp();
+        if (lane == 0) Dv[j] = dj;
+        const int i = j - 1 - lane;
+        if (i >= 0 && lane < bw) Dv[i] = fma(-W[offj + i], dj, Dv[i]);          // L[j][i]
+        __syncwarp();
+    }
+}
+
+// node nd of the trial state: nodes <- Exp(d[:6]) nodes ; vels <- vels + d[6:9]   (LieTensor.add_, A.1)
+__device__ __forceinline__ void small_retract_node(int nd, const double* __restrict__ Dv, const float* __restrict__ Xc,
+                                                   const float* __restrict__ Vc, float* __restrict__ Xt, float* __restrict__ Vt) {
+    double xi[6], Xd[7], Ed[7], Od[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi[k] = Dv[9 * nd + k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Xd[k] = (double)Xc[7 * nd + k];
+    se3_exp(xi, Ed);
+    se3_mul(Ed, Xd, Od);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Xt[7 * nd + k] = (float)Od[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Vt[3 * nd + k] = (float)((double)Vc[3 * nd + k] + Dv[9 * nd + 6 + k]);
+}
+
+struct SmallFactors {                    // the staged window (shared memory)
+    int E;
+    const int *ei, *ej;
+    const float *Zs, *r_vo, *J_vo, *sdrot, *sdtr, *sdv, *sdt, *r_imu, *J_rot;
+};
+// factor f at the trial state: its share of sum r^2 and of the unweighted (J D)^T (2 r + J D) of TrustRegion.update (A.4)
+__device__ __forceinline__ void small_trial_factor(int f, const SmallFactors& F, const float* __restrict__ Xt,
+                                                   const float* __restrict__ Vt, const double* __restrict__ Dv, double& lsum,
+                                                   double& qsum) {
+    if (f < F.E) {
+        const int i = F.ei[f], j = F.ej[f];
+        float r[6];
+        vo_factor(Xt + 7 * i, Xt + 7 * j, F.Zs + 7 * f, r, nullptr, nullptr);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) lsum += (double)r[k] * r[k];
+        const float* Jo = F.J_vo + 18 * f;
+        const float* ro = F.r_vo + 6 * f;
+        double d[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d[k] = Dv[9 * j + k] - Dv[9 * i + k];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            double jt = 0.0, jp = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                jt += (double)Jo[3 * p + q] * d[q] + (double)Jo[9 + 3 * p + q] * d[3 + q];
+                jp += (double)Jo[3 * p + q] * d[3 + q];
+            }
+            qsum += jt * (2.0 * (double)ro[p] + jt) + jp * (2.0 * (double)ro[3 + p] + jp);
+        }
+    } else {
+        const int i = f - F.E;
+        const float* Xa = Xt + 7 * i;
+        const float* Xb = Xa + 7;
+        float r[9];
+        rot_factor(Xa + 3, Xb + 3, F.sdrot + 4 * i, r + 3, nullptr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            r[k] = F.sdv[3 * i + k] - (Vt[3 * (i + 1) + k] - Vt[3 * i + k]);
+            r[6 + k] = (Xb[k] - Xa[k]) - (Vt[3 * i + k] * F.sdt[i] + F.sdtr[3 * i + k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) lsum += (double)r[k] * r[k];
+        const float* ro = F.r_imu + 9 * i;
+        const float* Jo = F.J_rot + 9 * i;
+        const double* Da = Dv + 9 * i;
+        const double* Db = Da + 9;
+        const double dt_ = (double)F.sdt[i];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double j1 = Da[6 + p] - Db[6 + p];
+            double j2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) j2 += (double)Jo[3 * p + q] * (Db[3 + q] - Da[3 + q]);
+            const double j3 = Db[p] - Da[p] - dt_ * Da[6 + p];
+            qsum += j1 * (2.0 * (double)ro[p] + j1) + j2 * (2.0 * (double)ro[3 + p] + j2) + j3 * (2.0 * (double)ro[6 + p] + j3);
+        }
+    }
+}
+
+// Speculative retries.  When a try is rejected PyPose re-damps the SAME normal equations and tries again, up to 16 times
+// (the shipped window does exactly that at convergence: 2 steps = 18 tries).  The damping of retry k+1 depends on retry k
+// only through the quality CLASS of TrustRegion.update, so the next SM_SPEC dampings are predicted (same class as the try
+// just rejected), factored, solved and evaluated at once, one warp each on its own band copy, and the controller then
+// consumes the results in order — the real lm_control runs for every consumed try and the batch is cut short the moment
+// its state departs from the prediction (or a try is accepted), so the sequence of decisions is exactly the sequential one.
+constexpr int SM_SPEC = SM_THREADS / 32;
+__host__ __device__ inline size_t small_slot_doubles(int N, int span) {
+    const int n = 9 * N, S = 9 * span + 9;
+    return ((size_t)n * S + 4 * (size_t)n + 5 * (size_t)N + 2) & ~(size_t)1;        // band, diagW, yv, dinv, Dv, trial state (10 N floats)
 }
 
 __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
@@ -96,10 +267,103 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
     __syncthreads();
     const double w0 = a.w[0], w1 = a.w[1], w2 = a.w[2], w3 = a.w[3];
     const int max_tries = (prm.max_steps > 0 ? prm.max_steps : 1) * (prm.reject + 1) + 1;
+    const SmallFactors FW{E, ei, ej, Zs, r_vo, J_vo, sdrot, sdtr, sdv, sdt, r_imu, J_rot};
+    // speculative retry slots behind the window (8-byte aligned)
+    const bool spec_ok = a.nspec > 1 && a.span <= 2;
+    double* slots = smem_d + ((small_smem_bytes(N, E) + 7) >> 3);
+    const size_t slot_doubles = small_slot_doubles(N, a.span);
+    __shared__ double sp_scale[SM_SPEC], sp_damp[SM_SPEC], sp_S[SM_SPEC], sp_Q[SM_SPEC];
+    __shared__ int sp_fail[SM_SPEC], sp_n, sp_take;
 
     for (int it = 0; it < max_tries; ++it) {
         if (!st.continual) break;                       // (uniform: written before the barrier that ends every try)
         __syncthreads();
+        if (spec_ok && !st.need_linearize) {
+            // ---- speculative retries (see SM_SPEC above): the normal equations are those of the rejected try --------------
+            const int cur = st.cur;
+            if (tid == 0) {
+                double damping = st.damping, down = st.down, scale = st.diag_scale;
+                const int left = prm.reject + 1 - st.reject_count;      // tries until the step accepts whatever comes
+                const int m = min(a.nspec, left > 1 ? left : 1);
+                // prediction: the retries fall into the same quality class as the try that was just rejected.  (At the noise
+                // floor — the shipped window's 16-reject step — that is quality ~ +1: the unweighted model predicts the tiny
+                // increase it then gets, so TrustRegion GROWS the radius on every rejected try.)
+                const int cls = st.quality > prm.high ? 2 : (st.quality > prm.low ? 1 : 0);
+                for (int k = 0; k < m; ++k) {
+                    sp_damp[k] = damping;
+                    scale *= (1.0 + damping);
+                    sp_scale[k] = scale;
+                    double radius = 1.0 / damping;                       // TrustRegion.update as in lm_control
+                    if (cls == 2) { radius *= prm.up; down = prm.down; }
+                    else if (cls == 1) { down = prm.down; }
+                    else { radius *= down; down *= prm.factor; }
+                    down = fmax(prm.tr_min, fmin(down, prm.tr_max));
+                    radius = fmax(prm.tr_min, fmin(radius, prm.tr_max));
+                    damping = 1.0 / radius;
+                }
+                sp_n = m; sp_take = -1;
+            }
+            __syncthreads();
+            const int w = tid >> 5, lane = tid & 31;
+            const int S = 9 * a.span + 9, ldw = S - 1, bwn = 9 * a.span;
+            double* sW = slots + (size_t)w * slot_doubles;               // band rows at stride S: W(row, col) = Wp[col + row * ldw]
+            double* Wp = sW + (S - 1);
+            double* sdiag = sW + (size_t)n * S;
+            double* sy = sdiag + n;
+            double* sdinv = sy + n;
+            double* sD = sdinv + n;
+            float* sX = reinterpret_cast<float*>(sD + n);
+            float* sV = sX + 7 * N;
+            if (w < sp_n) {
+                for (int idx = lane; idx < n * ldw; idx += 32) {
+                    const int i = idx / ldw, j = i - 1 - (idx - i * ldw);
+                    if (j >= 0) Wp[j + i * ldw] = A[i + (size_t)j * ld];
+                }
+                const double scale = sp_scale[w];
+                for (int k = lane; k < n; k += 32) { sdiag[k] = diag0[k] * scale; sy[k] = -gv[k]; }
+                __syncwarp();
+                const bool ok = small_factor_warp(Wp, ldw, sdiag, sy, sdinv, n, bwn, lane);
+                for (int k = lane; k < n; k += 32) sD[k] = sy[k];
+                __syncwarp();
+                small_backsolve_warp(Wp, ldw, sdinv, sD, n, bw, lane);
+                __syncwarp();
+                for (int nd = lane; nd < N; nd += 32) small_retract_node(nd, sD, X[cur], V[cur], sX, sV);
+                __syncwarp();
+                // the two sums in the reduction tree of block_sum<SM_THREADS> (factor f in thread f): same bits
+                double tl_ = 0.0, tq_ = 0.0;
+                for (int c = 0; c < SM_THREADS / 32; ++c) {
+                    double l = 0.0, q = 0.0;
+                    const int f = 32 * c + lane;
+                    if (f < E + M) small_trial_factor(f, FW, sX, sV, sD, l, q);
+                    l = warp_sum(l); q = warp_sum(q);
+                    l = __shfl_sync(0xffffffffu, l, 0); q = __shfl_sync(0xffffffffu, q, 0);
+                    if (lane == c) { tl_ = l; tq_ = q; }
+                }
+                tl_ = warp_sum(tl_); tq_ = warp_sum(tq_);
+                if (lane == 0) { sp_S[w] = tl_; sp_Q[w] = tq_; sp_fail[w] = ok ? 0 : 1; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = 0; k < sp_n; ++k) {
+                    if (st.damping != sp_damp[k]) break;                 // the controller left the predicted schedule
+                    st.active = 1; st.do_lin = 0; st.chol_fail = sp_fail[k]; st.tries_total += 1;
+                    st.diag_scale *= (1.0 + st.damping);
+                    const int before = st.cur;
+                    lm_control(&st, &prm, sp_fail[k] ? 0.0 : sp_S[k], sp_fail[k] ? 0.0 : sp_Q[k]);
+                    if (st.cur != before) sp_take = k;                   // accepted: slot k holds the new state
+                    if (st.need_linearize || !st.continual) break;       // the step is over (accepted or abandoned)
+                }
+            }
+            __syncthreads();
+            if (sp_take >= 0) {
+                const float* tX = reinterpret_cast<const float*>(slots + (size_t)sp_take * slot_doubles + (size_t)n * S + 4 * n);
+                const float* tV = tX + 7 * N;
+                for (int k = tid; k < 7 * N; k += NT) X[st.cur][k] = tX[k];
+                for (int k = tid; k < 3 * N; k += NT) V[st.cur][k] = tV[k];
+            }
+            __syncthreads();
+            continue;
+        }
         if (tid == 0) { st.active = 1; st.do_lin = st.need_linearize; st.chol_fail = 0; st.tries_total += 1; fail = 0; }
         __syncthreads();
         const int cur = st.cur, do_lin = st.do_lin;
@@ -276,61 +540,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
                 for (int k = tid; k < n; k += NT) { diagW[k] = diag0[k] * scale; yv[k] = -gv[k]; }
                 __syncthreads();
                 if (tid < 32) {
-                    const int lane = tid;
-                    bool ok = true;
-                    for (int c0 = 0; c0 < n; c0 += 9) {
-                        const int nbelow = min(bwn, n - c0 - 9);
-                        const bool is_row = lane < nbelow, is_rhs = lane == nbelow;
-                        const int i = c0 + 9 + lane;
-                        double D[9][9], isv[9], r[9];
-#pragma unroll
-                        for (int p = 0; p < 9; ++p) {
-                            D[p][p] = diagW[c0 + p];
-#pragma unroll
-                            for (int q = 0; q < p; ++q) D[p][q] = A[(c0 + q) + (c0 + p) * ld];
-                        }
-                        double* rowp = is_row ? A + c0 + i * ld : yv + c0;       // this lane's nine entries of the block column
-#pragma unroll
-                        for (int q = 0; q < 9; ++q) r[q] = (is_row || is_rhs) ? rowp[q] : 0.0;
-                        F4Diag<0>::run(D, isv, ok);
-                        f4_row_solve(r, D, isv);
-#pragma unroll
-                        for (int p = 0; p < 9; ++p) {
-                            dinv[c0 + p] = isv[p];
-#pragma unroll
-                            for (int q = 0; q < p; ++q) A[(c0 + q) + (c0 + p) * ld] = D[p][q];
-                        }
-                        if (is_row || is_rhs) {
-#pragma unroll
-                            for (int q = 0; q < 9; ++q) rowp[q] = r[q];
-                        }
-                        __syncwarp();
-                        // trailing update inside the band: W[i][j'] -= sum_q L[i][q] L[j'][q] for the rows j' <= i below the block
-                        // (nine rows j' at a time, all accumulators independent: the loads are issued together, not one
-                        // dependent load -> fma chain per entry)
-                        for (int u0 = 0; u0 < nbelow; u0 += 9) {
-                            double s_[9];
-#pragma unroll
-                            for (int u = 0; u < 9; ++u) s_[u] = 0.0;
-#pragma unroll
-                            for (int q = 0; q < 9; ++q) {
-#pragma unroll
-                                for (int u = 0; u < 9; ++u) {
-                                    const int uu = u0 + u < nbelow ? u0 + u : u0;
-                                    s_[u] = fma(r[q], A[c0 + q + (c0 + 9 + uu) * ld], s_[u]);       // L[j'][c0 + q], broadcast
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 9; ++u) {
-                                const int uu = u0 + u;
-                                if (uu >= nbelow) continue;
-                                if (is_rhs) yv[c0 + 9 + uu] -= s_[u];
-                                else if (is_row && lane == uu) diagW[i] -= s_[u];
-                                else if (is_row && lane > uu) A[(c0 + 9 + uu) + i * ld] -= s_[u];
-                            }
-                        }
-                        __syncwarp();
-                    }
+                    const bool ok = small_factor_warp(A, ld, diagW, yv, dinv, n, bwn, tid);
                     if (!ok) fail = 1;
                 }
                 __syncthreads();
@@ -372,17 +582,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
         for (int k = tid; k < n; k += NT) Dv[k] = yv[k];
         __syncthreads();
         if (warp_path) {
-            if (tid < 32) {
-                int offj = (n - 1) * ld;
-                for (int j = n - 1; j >= 0; --j, offj -= ld) {
-                    const double dj = Dv[j] * dinv[j];
-                    __syncwarp();
-                    if (tid == 0) Dv[j] = dj;
-                    const int i = j - 1 - tid;
-                    if (i >= 0 && tid < bw) Dv[i] = fma(-A[offj + i], dj, Dv[i]);          // L[j][i]
-                    __syncwarp();
-                }
-            }
+            if (tid < 32) small_backsolve_warp(A, ld, dinv, Dv, n, bw, tid);
             __syncthreads();
         } else {
             for (int j = n - 1; j >= 0; --j) {
@@ -396,19 +596,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
         }
         SMALL_T(4);
         // ---- retract to the trial state (LieTensor.add_, A.1) --------------------------------------------------------------
-        for (int nd = tid; nd < N; nd += NT) {
-            double xi[6], Xd[7], Ed[7], Od[7];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) xi[k] = Dv[9 * nd + k];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) Xd[k] = (double)X[cur][7 * nd + k];
-            se3_exp(xi, Ed);
-            se3_mul(Ed, Xd, Od);
-#pragma unroll
-            for (int k = 0; k < 7; ++k) X[cur ^ 1][7 * nd + k] = (float)Od[k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) V[cur ^ 1][3 * nd + k] = (float)((double)V[cur][3 * nd + k] + Dv[9 * nd + 6 + k]);
-        }
+        for (int nd = tid; nd < N; nd += NT) small_retract_node(nd, Dv, X[cur], V[cur], X[cur ^ 1], V[cur ^ 1]);
         __syncthreads();
         SMALL_T(5);
         // ---- trial residuals and the unweighted (J D)^T (2 r + J D) of TrustRegion.update (A.4) ---------------------------
@@ -416,57 +604,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_lm_small(SmallArgs a) {
             double lsum = 0.0, qsum = 0.0;
             const float* Xt = X[cur ^ 1];
             const float* Vt = V[cur ^ 1];
-            for (int f = tid; f < E + M; f += NT) {
-                if (f < E) {
-                    const int i = ei[f], j = ej[f];
-                    float r[6];
-                    vo_factor(Xt + 7 * i, Xt + 7 * j, Zs + 7 * f, r, nullptr, nullptr);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) lsum += (double)r[k] * r[k];
-                    const float* Jo = J_vo + 18 * f;
-                    const float* ro = r_vo + 6 * f;
-                    double d[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) d[k] = Dv[9 * j + k] - Dv[9 * i + k];
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        double jt = 0.0, jp = 0.0;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            jt += (double)Jo[3 * p + q] * d[q] + (double)Jo[9 + 3 * p + q] * d[3 + q];
-                            jp += (double)Jo[3 * p + q] * d[3 + q];
-                        }
-                        qsum += jt * (2.0 * (double)ro[p] + jt) + jp * (2.0 * (double)ro[3 + p] + jp);
-                    }
-                } else {
-                    const int i = f - E;
-                    const float* Xa = Xt + 7 * i;
-                    const float* Xb = Xa + 7;
-                    float r[9];
-                    rot_factor(Xa + 3, Xb + 3, sdrot + 4 * i, r + 3, nullptr);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        r[k] = sdv[3 * i + k] - (Vt[3 * (i + 1) + k] - Vt[3 * i + k]);
-                        r[6 + k] = (Xb[k] - Xa[k]) - (Vt[3 * i + k] * sdt[i] + sdtr[3 * i + k]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) lsum += (double)r[k] * r[k];
-                    const float* ro = r_imu + 9 * i;
-                    const float* Jo = J_rot + 9 * i;
-                    const double* Da = Dv + 9 * i;
-                    const double* Db = Da + 9;
-                    const double dt_ = (double)sdt[i];
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const double j1 = Da[6 + p] - Db[6 + p];
-                        double j2 = 0.0;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) j2 += (double)Jo[3 * p + q] * (Db[3 + q] - Da[3 + q]);
-                        const double j3 = Db[p] - Da[p] - dt_ * Da[6 + p];
-                        qsum += j1 * (2.0 * (double)ro[p] + j1) + j2 * (2.0 * (double)ro[3 + p] + j2) + j3 * (2.0 * (double)ro[6 + p] + j3);
-                    }
-                }
-            }
+            for (int f = tid; f < E + M; f += NT) small_trial_factor(f, FW, Xt, Vt, Dv, lsum, qsum);
             const double S = block_sum<SM_THREADS>(lsum, red);
             const double Q = block_sum<SM_THREADS>(qsum, red2);
             if (tid == 0) lm_control(&st, &prm, S, Q);
@@ -546,7 +684,23 @@ extern "C" int islam_pvgo_small_run(int32_t B, int32_t N, int32_t E, const int32
     for (int k = 0; k < 4; ++k) a.w[k] = w[k];
     a.prm = *prm;
     a.out_nodes = out_nodes; a.out_vels = out_vels; a.out_state = out_state; a.voP = voP; a.tl = tl; a.rl = rl; a.gt = gt; a.gr = gr;
-    const size_t smem = islam::small_smem_bytes(N, E);
+    size_t smem = islam::small_smem_bytes(N, E);
+    {
+        // speculative retry slots: as many (<= SM_SPEC) as fit behind the window in one SM's shared memory
+        static int max_optin = -1;
+        if (max_optin < 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) max_optin = 0;
+        }
+        const char* env = std::getenv("ISLAM_SMALL_SPEC");
+        const size_t base = (smem + 7) & ~(size_t)7, slot = islam::small_slot_doubles(N, span) * sizeof(double);
+        long long fit = span <= 2 ? ((long long)max_optin - 2048 - (long long)base) / (long long)slot : 0;
+        if (env) fit = std::min<long long>(fit, std::atoi(env));
+        a.nspec = (int)std::max<long long>(0, std::min<long long>(fit, islam::SM_SPEC));
+        if (a.nspec > 1) smem = base + a.nspec * slot;
+        else a.nspec = 0;
+    }
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(islam::k_lm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -118,3 +118,35 @@ def test_batch_of_windows_equals_window_by_window():
         assert torch.equal(tl[b].cpu(), one[0].cpu())
         ref = po.SparseLM(gs[b], np.float64).run()
         assert po.rel_pose_error(nodes[b].numpy(), ref.aligned(gs[b].init_nodes[0])[0])['rel'] <= 1e-5
+
+
+def _with_spec(g, slots, **kw):
+    """run_pvgo with the speculative retry slots capped (0 = the plain sequential loop)."""
+    os.environ['ISLAM_SMALL_SPEC'] = str(slots)
+    try:
+        out = run_pvgo(*_args(g), radius=kw.pop('radius', g.radius), loss_weight=g.loss_weight, **kw)
+        return out, run_pvgo.last_state
+    finally:
+        del os.environ['ISLAM_SMALL_SPEC']
+
+
+@pytest.mark.parametrize('case', ['plateau_storm', 'perturbed'])
+def test_speculative_retries_are_bit_identical_to_the_sequential_loop(case):
+    """csrc/small.cuh SM_SPEC: rejected tries are re-damped, factored and evaluated eight at a time, then consumed in order by
+    the real controller.  Same decisions, same try counts and the SAME BITS as one try after the other."""
+    if case == 'plateau_storm':
+        g, kw = synth.window(), {}
+    else:
+        g = synth.window(N=12)
+        d = np.random.default_rng(1).standard_normal((g.N, 6)) * np.array([2, 2, 2, 0.8, 0.8, 0.8])
+        g.init_nodes = lie.se3_retract(g.init_nodes.astype(np.float64), d).astype(np.float32)
+        kw = dict(radius=1e6, use_scheduler=False, max_steps=5)
+    (tl0, rl0, n0, v0, _), s0 = _with_spec(g, 0, **dict(kw))
+    for slots in (8, 3):
+        (tl1, rl1, n1, v1, _), s1 = _with_spec(g, slots, **dict(kw))
+        assert (s1.steps_done, s1.tries_total, s1.reject_count, s1.info) == (s0.steps_done, s0.tries_total, s0.reject_count, s0.info)
+        assert s1.loss == s0.loss and s1.damping == s0.damping
+        assert np.array_equal(np.asarray(n0), np.asarray(n1)) and np.array_equal(np.asarray(v0), np.asarray(v1))
+        assert torch.equal(tl0, tl1) and torch.equal(rl0, rl1)
+    if case == 'plateau_storm':
+        assert s0.tries_total == s0.steps_done + 16        # the case does reject tries

@@ -24,6 +24,10 @@ def e2e(n=200):
 
 ms, st = e2e()
 print(f'run_pvgo, 9-pose window, one-launch path: {ms:7.4f} ms per call end to end ({st.steps_done} LM steps, {st.tries_total} tries)')
+os.environ['ISLAM_SMALL_SPEC'] = '0'
+ms1, st1 = e2e()
+del os.environ['ISLAM_SMALL_SPEC']
+print(f'run_pvgo, same, speculative retries off   : {ms1:7.4f} ms per call end to end ({st1.steps_done} LM steps, {st1.tries_total} tries)')
 os.environ['ISLAM_NO_SMALL'] = '1'
 ms2, st2 = e2e(50)
 del os.environ['ISLAM_NO_SMALL']
