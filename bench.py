@@ -22,6 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('TORCH_NCCL_HIGH_PRIORITY', '1')      # islam_b200/dist.py: look-ahead broadcasts of the distributed dense root
 
 LM_ITERS = 10                 # optimizer.step calls per step (StopOnPlateau's max steps, pvgo.py:172)
 WORKLOAD = ('C2: 5000 poses / 39964 VO edges (band 8) + 4999 IMU pairs = 49962 factors, 284775 rows; '
@@ -334,12 +335,83 @@ def run_ours(args, rank, world, local_rank):
         out['cpu_baseline'] = {'value': 10 / t_cpu, 'unit': 'LM it/s', 'factors_per_s': 10 / t_cpu * F, 'cores': _cpu_threads(), 'kind': 'port',
                                'sample': '10 LM iterations of C2 (oracle.SparseLM float64: single-threaded NumPy assembly + LAPACK banded '
                                          'Cholesky on the BLAS thread pool, same normal equations; literal dense PyPose needs 324 GB at C2)'}
+    if not args.no_extras:
+        try:
+            from islam_b200.dist import ShardedPVGO as _Sh
+            extras = _other_configs(rank, world, dev, _Sh)
+        except Exception as exc:                                # never lose the headline to an extra
+            extras = {'error': f'{type(exc).__name__}: {exc}'}
+        out['other_configs'] = extras
     if rank == 0:
         _emit(out)
     if world > 1:
         sh.release_graph()
         torch.cuda.synchronize()
         dist.destroy_process_group()
+
+
+def _other_configs(rank, world, dev, sh_cls):
+    """The other BASELINE.json configs that have a story of their own, measured beside the headline (never part of `value`):
+    C5's back-end share — run_pvgo on the shipped 9-pose window, host tensors in and out (N = 1 only) — and C4, 50 000 poses
+    with 2 000 loop closures (dense root of 24 519 unknowns): ms per LM iteration, on N GPUs with the root factored by all
+    ranks together (islam_b200/dist.py).  CUDA events / wall clock after warm-up, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from islam_b200 import synth
+    out = {}
+    if world == 1:
+        from islam_b200 import pvgo as ipvgo
+        w = synth.window()
+        t = lambda a_: torch.as_tensor(a_).pin_memory()
+        a = [t(w.init_nodes), t(w.init_vels), t(w.vo_motions), torch.as_tensor(w.links), t(w.dts), t(w.imu_drots), t(w.imu_dtrans),
+             t(w.imu_dvels)]
+        for _ in range(10):
+            ipvgo.run_pvgo(*a, device=dev, radius=w.radius, loss_weight=w.loss_weight)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(100):
+            ipvgo.run_pvgo(*a, device=dev, radius=w.radius, loss_weight=w.loss_weight)
+        torch.cuda.synchronize()
+        st = ipvgo.run_pvgo.last_state
+        out['C5_window_run_pvgo'] = {'ms_per_call': (time.perf_counter() - t0) / 100 * 1e3, 'poses': int(w.N), 'lm_steps': st.steps_done,
+                                     'tries': st.tries_total, 'api': 'run_pvgo, host tensors in and out, StopOnPlateau (pvgo.py:122-205)'}
+    g4 = synth.config4()
+    tries = 3
+    if world == 1:
+        from islam_b200.solver import PVGOSolver
+        s4 = PVGOSolver(g4.N, g4.links, device=dev)
+        step = s4.lm_step
+    else:
+        s4w = sh_cls(g4.N, g4.links, dev)
+        s4 = s4w.s
+
+        def step():
+            s4w.lm_try()
+            return s4.lm_state()
+    (s4w if world > 1 else s4).set_problem(g4.vo_motions, g4.imu_drots, g4.imu_dtrans, g4.imu_dvels, g4.dts, g4.loss_weight)
+    (s4w if world > 1 else s4).set_state(g4.init_nodes, g4.init_vels)
+    (s4w if world > 1 else s4).lm_reset(radius=g4.radius, max_steps=tries + 1, use_scheduler=0)
+    st = step()                                           # warm-up (first touch of 4.8 GB of factor, NCCL channels)
+    n0 = st.tries_total
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s4.stream):
+        e0.record()
+        for _ in range(tries):
+            st = step()
+        e1.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    out['C4_loop_closures'] = {'ms_per_lm_iteration': float(tm.item()) / max(1, st.tries_total - n0), 'n_gpus': world,
+                               'poses': int(g4.N), 'loop_closures': 2000, 'fronts': int(s4.dims.F),
+                               'loss_after': st.loss, 'info': st.info,
+                               'how': 'dense root factored block-column-cyclically by all ranks, NCCL broadcast of each factored block'
+                                      if world > 1 else 'dense root on one GPU (csrc/dense_root.cuh)'}
+    return out
+
 
 
 def _emit(obj):
@@ -361,6 +433,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C4 / C5 side measurements (other_configs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -6,7 +6,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1000 -c 54 --csv \
-    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_factor3 -s 23 -c 1 -o gpurun_out/f3_l3 -f python tools/solve_loop.py 3 > gpurun_out/ncu_f3.log 2>&1
 timeout 200 python tools/level_timeline.py > gpurun_out/timeline.log 2>&1
 timeout 200 python tools/phase_clocks.py 1 4 64 256 512 > gpurun_out/phase.log 2>&1
