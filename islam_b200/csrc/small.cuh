@@ -79,6 +79,7 @@ __device__ __forceinline__ bool small_factor_warp(double* __restrict__ W, int ld
         for (int q = 0; q < 9; ++q) r[q] = (is_row || is_rhs) ? rowp[q] : 0.0;
         F4Diag<0>::run(D, isv, ok);
         f4_row_solve(r, D, isv);
+        __syncwarp();                                   // every lane has read the block before any lane overwrites it with L
 #pragma unroll
         for (int p = 0; p < 9; ++p) {
             dinv[c0 + p] = isv[p];
