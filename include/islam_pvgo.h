@@ -20,7 +20,7 @@
  *     CUDA-graph capturable except the functions marked "synchronises".
  *   - Return value: 0 ok, <0 invalid argument / unsupported, >0 cudaError_t.  islam_pvgo_create: -2 bad edge list,
  *     -5 boundary too wide for the back-substitution kernel, -6 a single-GPU-only call on an n_parts > 1 handle
- *     (islam_pvgo_lm_try / _lm_run / _solve / _profile_try / _set_reproj), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
+ *     (islam_pvgo_lm_try / _lm_run / _solve / _profile_try), -7 more than 128 GB of factor panels, -8 graph too large for the 29-bit block offsets.
  *     islam_pvgo_lm_step / _lm_run: -9 the step / loop did not close within its worst-case try budget.
  *     LM state `info`: 1 Cholesky failed (PyPose's "Linear solver failed"), 2 a multi-GPU peer never answered, 3 a device-side
  *     wait inside the back-substitution timed out (wedged device); 2 and 3 also clear `continual`.
@@ -104,7 +104,8 @@ int islam_pvgo_set_problem(islam_pvgo* h, const float* vo_motions /* E x 7 */, c
  * SparseReprojectionLoss): per consecutive pair i, n_points camera-frame points of pose i (point3d, M x n_points x 3) and
  * their target pixels in the camera at pose i+1 (M x n_points x 2), both device pointers (copied); intrinsics fx, fy, cx, cy
  * and the rgb2imu pose (7) are host arrays; info_w = (loss_weight[4] / n_points)^2.  motion[0] is the constant 0.1 as at
- * pvgo.py:57 (zero Jacobian for pair 0).  n_points = 0 removes the factor.  Single GPU only (-6 with n_parts > 1). */
+ * pvgo.py:57 (zero Jacobian for pair 0).  n_points = 0 removes the factor.  Multi-GPU: every rank stages all pairs and evaluates
+ * the ones it owns, like the IMU factors. */
 int islam_pvgo_set_reproj(islam_pvgo* h, const float* point3d, const float* target, int32_t n_points,
                           const float intrinsics[4], const float rgb2imu[7], double info_w, void* stream);
 int islam_pvgo_get_reproj_residuals(islam_pvgo* h, float* reprojerr /* M x 2 n_points */, void* stream);

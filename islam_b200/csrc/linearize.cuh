@@ -558,7 +558,7 @@ assemble_pairs_block(int blk, const LMState* __restrict__ st, ProblemView pv, Li
                 if (a >= 6) v -= pv.w[1];
             }
             if (a >= 6 && b < 3 && a - 6 == b) v -= pv.w[3] * dt;   // (v_lo, tau_hi)
-            if (pv.rp_n > 0 && a < 6 && b < 6) v -= pv.w[4] * lb.S_rp[36 * (size_t)lo + 6 * a + b];
+            if (pv.rp_n > 0 && adj && a < 6 && b < 6) v -= pv.w[4] * lb.S_rp[36 * (size_t)lo + 6 * a + b];      // owner's share (multi-GPU)
         }
         Ho[81 * (size_t)p + 9 * a + b] = v;
     }

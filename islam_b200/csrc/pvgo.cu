@@ -601,7 +601,6 @@ extern "C" int islam_pvgo_set_state(islam_pvgo* h, const float* nodes, const flo
 extern "C" int islam_pvgo_set_reproj(islam_pvgo* h, const float* point3d, const float* target, int32_t n_points,
                                      const float intrinsics[4], const float rgb2imu[7], double info_w, void* stream) {
     if (!h || n_points < 0) return -1;
-    if (h->opts.n_parts > 1 && n_points > 0) return -6;            // single-GPU only
     cudaStream_t s = (cudaStream_t)stream;
     const Plan& p = h->plan;
     const int was = h->nblk_rp;

@@ -285,34 +285,38 @@ def run_pvgo(init_nodes, init_vels, vo_motions, links, dts, imu_drots, imu_dtran
         return out + (covs,)
 
     graph = PoseVelGraph(init_nodes, init_vels, reproj, links=links, device=device)
-    # one host -> device transfer of the VO motions serves both the optimisation (detached, pvgo.py:146) and the outer
-    # loss (autograd-connected, pvgo.py:186-187); .to() is differentiable, so the gradient still reaches the caller's tensor
-    vo_dev = _plain(vo_motions).to(device=graph._device, dtype=torch.float32, non_blocking=True)
-    graph._ensure(links, vo_dev.detach(), imu_drots, imu_dtrans, imu_dvels, dts, loss_weight)
-    s = graph.solver
-    # pvgo.py:169-180: LM(min=1e-4) + Cholesky + TrustRegion(radius) + StopOnPlateau(steps=10, patience=3, 1e-3)
-    s.lm_reset(radius=float(radius), lm_min=1e-4, max_steps=int(max_steps), patience=int(patience),
-               decreasing=float(decreasing), use_scheduler=1 if use_scheduler else 0)
-    st = s.lm_run()
-    if st.info == 1:
-        print('Linear solver failed. Breaking optimization step...')            # PyPose's message (A.4)
-    elif st.info:
-        raise IslamError(f'the device-side LM loop reported info={st.info} (see include/islam_pvgo.h)')
+    # the whole call runs on the solver's stream (uploads, LM loop, outer loss, downloads): ordered ONCE after whatever the
+    # caller's stream still has in flight (device-resident inputs), no cross-stream events per step; synchronised at the end
+    graph.solver.stream.wait_stream(torch.cuda.current_stream(graph._device))
+    with torch.cuda.stream(graph.solver.stream):
+        # one host -> device transfer of the VO motions serves both the optimisation (detached, pvgo.py:146) and the outer
+        # loss (autograd-connected, pvgo.py:186-187); .to() is differentiable, so the gradient still reaches the caller's tensor
+        vo_dev = _plain(vo_motions).to(device=graph._device, dtype=torch.float32, non_blocking=True)
+        graph._ensure(links, vo_dev.detach(), imu_drots, imu_dtrans, imu_dvels, dts, loss_weight)
+        s = graph.solver
+        # pvgo.py:169-180: LM(min=1e-4) + Cholesky + TrustRegion(radius) + StopOnPlateau(steps=10, patience=3, 1e-3)
+        s.lm_reset(radius=float(radius), lm_min=1e-4, max_steps=int(max_steps), patience=int(patience),
+                   decreasing=float(decreasing), use_scheduler=1 if use_scheduler else 0)
+        st = s.lm_run()
+        if st.info == 1:
+            print('Linear solver failed. Breaking optimization step...')            # PyPose's message (A.4)
+        elif st.info:
+            raise IslamError(f'the device-side LM loop reported info={st.info} (see include/islam_pvgo.h)')
 
-    if target == 'vo':                                                          # pvgo.py:186-189
-        trans_loss, rot_loss = graph.vo_loss(links, vo_dev)
-    elif target == 'imu':
-        trans_loss, rot_loss = graph.imu_loss(imu_drots, imu_dvels)
-    else:
-        raise ValueError(f'unknown target {target!r}')
+        if target == 'vo':                                                          # pvgo.py:186-189
+            trans_loss, rot_loss = graph.vo_loss(links, vo_dev)
+        elif target == 'imu':
+            trans_loss, rot_loss = graph.imu_loss(imu_drots, imu_dvels)
+        else:
+            raise ValueError(f'unknown target {target!r}')
 
-    nodes, vels = graph.align_to(_plain(init_nodes)[0])                         # pvgo.py:195
-    # nodes.cpu(), vels.cpu() (pvgo.py:196-197) as two asynchronous copies into pinned memory and ONE synchronisation
-    nodes_h = torch.empty(nodes.shape, dtype=nodes.dtype, pin_memory=True)
-    vels_h = torch.empty(vels.shape, dtype=vels.dtype, pin_memory=True)
-    nodes_h.copy_(_plain(nodes).detach(), non_blocking=True)
-    vels_h.copy_(vels.detach(), non_blocking=True)
-    torch.cuda.current_stream(graph._device).synchronize()
+        nodes, vels = graph.align_to(_plain(init_nodes)[0])                         # pvgo.py:195
+        # nodes.cpu(), vels.cpu() (pvgo.py:196-197) as two asynchronous copies into pinned memory and ONE synchronisation
+        nodes_h = torch.empty(nodes.shape, dtype=nodes.dtype, pin_memory=True)
+        vels_h = torch.empty(vels.shape, dtype=vels.dtype, pin_memory=True)
+        nodes_h.copy_(_plain(nodes).detach(), non_blocking=True)
+        vels_h.copy_(vels.detach(), non_blocking=True)
+        torch.cuda.current_stream(graph._device).synchronize()
     nodes = _wrap_like(init_nodes, nodes_h, 'SE3_type')
     vels = vels_h
     covs = {'vo_rot': vo_rot_infos, 'imu_rot': imu_rot_infos, 'vo_trans': vo_trans_infos,

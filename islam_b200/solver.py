@@ -63,10 +63,14 @@ class PVGOSolver:
         return C.c_void_p(self.stream.cuda_stream)
 
     def _enter(self):
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self.stream:                        # (run_pvgo works on the solver's stream: nothing to order)
+            self.stream.wait_stream(cur)
 
     def _exit(self):
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self.stream:
+            cur.wait_stream(self.stream)
 
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def _solver(g, **kw):
     s = PVGOSolver(g.N, g.links, **kw)
-    s.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
+    s.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight, reproj=_reproj_of(g, 'cuda'))
     s.set_state(g.init_nodes, g.init_vels)
     return s
 
@@ -138,7 +138,28 @@ def test_window_with_scheduler_matches_oracle():
 
 _MG_GRAPHS = {'band8': (lambda: synth.config2(N=600, band=8), 5),
               # 70 loop closures => a dense root of ~140 poses (~850 unknowns, 7 tile columns), csrc/dense_root.cuh
-              'lcdense': (lambda: synth.config4(N=2500, n_lc=70, min_gap=100), 4)}
+              'lcdense': (lambda: synth.config4(N=2500, n_lc=70, min_gap=100), 4),
+              # the optional 5th residual group (pvgo.py:53-61): every rank evaluates the reprojection factors of the pairs it owns
+              'band8rp': (lambda: _with_reproj(synth.config2(N=400, band=8)), 4)}
+
+
+def _with_reproj(g, n_points=12, weight=2.0):
+    g.extra['reproj'] = synth.reproj_data(g, n_points, weight=weight)
+    g.loss_weight = tuple(g.loss_weight[:4]) + (weight,)
+    return g
+
+
+def _reproj_of(g, dev):
+    """An object shaped like dense_ba.SparseReprojectionLoss (attributes only), or None."""
+    rp = g.extra.get('reproj') if hasattr(g, 'extra') else None
+    if rp is None:
+        return None
+    import types
+    fx, fy, cx, cy = [float(v) for v in rp['K']]
+    t = torch.as_tensor
+    return types.SimpleNamespace(N=int(rp['point3d'].shape[1]), point3d=t(rp['point3d']).to(dev), target=t(rp['target']).to(dev),
+                                 K=torch.tensor([fx, 0, cx, 0, fy, cy, 0, 0, 1], dtype=torch.float32).view(3, 3).to(dev),
+                                 rgb2imu_pose=t(rp['rgb2imu']).to(dev))
 
 
 def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False):
@@ -155,7 +176,7 @@ def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False):
     mk, steps = _MG_GRAPHS[name]
     g = mk()
     sh = ShardedPVGO(g.N, g.links, dev, exchange=exchange)
-    sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight)
+    sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight, reproj=_reproj_of(g, dev))
     sh.set_state(g.init_nodes, g.init_vels)
     sh.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
     st = sh.lm_run()
@@ -194,7 +215,7 @@ def test_sharded_lm_matches_single_gpu_and_oracle(world, exchange, tmp_path):
     _check_sharded(out, 'band8')
 
 
-@pytest.mark.parametrize('world,name', [(2, 'band8'), (2, 'lcdense'), (4, 'lcdense')])
+@pytest.mark.parametrize('world,name', [(2, 'band8'), (2, 'lcdense'), (4, 'lcdense'), (2, 'band8rp')])
 def test_sharded_ranks_on_one_gpu(world, name, tmp_path):
     """The N>1 path on a ONE-GPU box: `world` processes share cuda:0 and exchange through gloo (host-staged), so the
     sharded kernels — stage 1 / 2 of the separator fronts, the partial root, the block-column-cyclic dense-root Cholesky with
@@ -297,6 +318,40 @@ def test_config4_dense_root_matches_oracle():
     n, _ = s.align(g.init_nodes[0])
     rn, _ = ref.aligned(g.init_nodes[0])
     assert po.rel_pose_error(n.cpu().numpy(), rn)['rel'] <= 1e-5
+
+
+def _dense_reference_solve(s, g, scale):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    Hd, Ho, gg, pairs = [t.cpu().numpy() for t in s.normal_equations()]
+    N = g.N
+    rows, cols, vals = [], [], []
+    ar = np.arange(9)
+    for n in range(N):
+        rows.append(np.repeat(9 * n + ar, 9)); cols.append(np.tile(9 * n + ar, 9)); vals.append(Hd[n].ravel())
+    for p_, (a, b) in enumerate(pairs):
+        rows.append(np.repeat(9 * a + ar, 9)); cols.append(np.tile(9 * b + ar, 9)); vals.append(Ho[p_].ravel())
+        rows.append(np.repeat(9 * b + ar, 9)); cols.append(np.tile(9 * a + ar, 9)); vals.append(Ho[p_].T.ravel())
+    H = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(9 * N, 9 * N)).tocsc()
+    d = np.clip(H.diagonal(), 1e-4, 1e32) * scale
+    A = (H + sp.diags(d - H.diagonal())).tocsc()
+    return spla.splu(A).solve(-gg.reshape(-1)).reshape(-1, 9)
+
+
+@pytest.mark.parametrize('N,n_lc,gap', [(600, 34, 40), (900, 52, 40), (1500, 95, 60), (3000, 210, 100)])
+def test_dense_root_sizes_against_sparse_lu(N, n_lc, gap):
+    """The dense-root kernels (csrc/dense_root.cuh: potrf with explicit inverse, DMMA panel solve, TMA-staged K = 128 update,
+    multi-CTA back-substitution) on roots of different sizes — ragged last 64- and 128-column blocks, one to a dozen tile
+    columns — against SciPy's sparse LU on the same damped normal equations."""
+    g = synth.config4(N=N, n_lc=n_lc, min_gap=gap)
+    s = _solver(g)
+    assert s.dims.root_pivots >= 60
+    s.linearize()
+    scale = 1.0 + 1e-4
+    Dref = _dense_reference_solve(s, g, scale)
+    D, info = s.solve(scale)
+    assert info == 0
+    assert np.abs(D.cpu().numpy() - Dref).max() <= 1e-7 * np.abs(Dref).max()
 
 
 def test_config4_large_dense_root_properties():
