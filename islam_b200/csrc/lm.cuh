@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(256) k_reduce2(const LMState* __restrict__ st,
     for (int k = threadIdx.x; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
     s = block_sum<256>(s, sh);
     q = block_sum<256>(q, sh2);
-    if (threadIdx.x == 0) { out[0] = s; out[1] = q; }
+    // multi-GPU trial sums (lin_only == 0 is only used there): a Cholesky that failed on THIS rank (a private front, or the
+    // block of the distributed dense root this rank owns) must fail the try on EVERY rank, or the ranks take different
+    // decisions and the next collective never completes.  The flag travels as a NaN in the sum (lm_control_shared).
+    if (threadIdx.x == 0) { out[0] = (!lin_only && st->chol_fail) ? __longlong_as_double(0x7ff8000000000000LL) : s; out[1] = q; }
 }
 
 // after the (possibly all-reduced) linearisation loss is known
@@ -140,9 +143,14 @@ __device__ __forceinline__ void lm_control(LMState* st, const islam_lm_params* _
         lm_end_step(st, p);
     }
 }
+// multi-GPU: the summed trial loss is NaN when any rank's factorisation failed (k_reduce2 / k_end_try_p2p)
+__device__ __forceinline__ void lm_control_shared(LMState* st, const islam_lm_params* __restrict__ pp, double s, double q) {
+    if (s != s) st->chol_fail = 1;
+    lm_control(st, pp, s, q);
+}
 __global__ void k_lm_control(LMState* st, const islam_lm_params* __restrict__ pp, const double* __restrict__ sums) {
     if (threadIdx.x != 0 || !st->active) return;
-    lm_control(st, pp, sums[0], sums[1]);
+    lm_control_shared(st, pp, sums[0], sums[1]);
 }
 
 // single GPU: closes the try in ONE launch — deterministic sum of the trial partials, then the controller
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256) k_end_try_p2p(LMState* st, const islam_lm
     for (int k = tid; k < nparts; k += 256) { s += part[2 * k]; q += part[2 * k + 1]; }
     s = block_sum<256>(s, sh);
     q = block_sum<256>(q, sh2);
-    if (tid == 0) { my[0] = s; my[1] = q; seq_s = ++(*seq_ctr); failed = 0; }
+    if (tid == 0) { my[0] = st->chol_fail ? __longlong_as_double(0x7ff8000000000000LL) : s; my[1] = q; seq_s = ++(*seq_ctr); failed = 0; }
     __syncthreads();
     const unsigned long long seq = seq_s;
     const int slot = (int)(seq & 1);
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(256) k_end_try_p2p(LMState* st, const islam_lm
     double S = 0.0, Q = 0.0;
     for (int r = 0; r < G; ++r) { S += in_s[r]; Q += in_q[r]; }
     sums[0] = S; sums[1] = Q;
-    lm_control(st, pp, S, Q);
+    lm_control_shared(st, pp, S, Q);
 }
 
 // lm_reset without a host round trip: the parameters travel as a kernel argument into device memory, the state is

@@ -162,7 +162,7 @@ def _reproj_of(g, dev):
                                  rgb2imu_pose=t(rp['rgb2imu']).to(dev))
 
 
-def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False):
+def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False, lm_kw=None):
     import os
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -178,9 +178,11 @@ def _mg_worker(rank, world, port, out, exchange, name='band8', one_gpu=False):
     sh = ShardedPVGO(g.N, g.links, dev, exchange=exchange)
     sh.set_problem(g.vo_motions, g.imu_drots, g.imu_dtrans, g.imu_dvels, g.dts, g.loss_weight, reproj=_reproj_of(g, dev))
     sh.set_state(g.init_nodes, g.init_vels)
-    sh.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
+    sh.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0, **(lm_kw or {}))
     st = sh.lm_run()
     n, v = sh.get_state()
+    if lm_kw:                                    # per-rank view of the LM state (failure tests)
+        torch.save(dict(info=st.info, steps=st.steps_done, tries=st.tries_total, loss=st.loss), f'{out}.{rank}')
     if rank == 0:
         torch.save(dict(nodes=n.cpu(), vels=v.cpu(), loss=st.loss, steps=st.steps_done, rejects=st.reject_count, info=st.info,
                         root_n=sh.root_n, n_shared=sh.s.dims.n_shared_fronts), out)
@@ -225,6 +227,22 @@ def test_sharded_ranks_on_one_gpu(world, name, tmp_path):
     mp.spawn(_mg_worker, args=(world, 29571 + world + len(name), out, 'nccl', name, True), nprocs=world, join=True)
     r = _check_sharded(out, name, loss_rtol=1e-8)
     assert (r['root_n'] > 0) == (name == 'lcdense')
+
+
+@pytest.mark.parametrize('name', ['band8', 'lcdense'])
+def test_sharded_failed_cholesky_is_seen_by_every_rank(name, tmp_path):
+    """A factorisation that fails (every pivot diagonal clamped to -1: not SPD) must abandon the step on EVERY rank — with
+    the distributed dense root only the owner of a block sees its non-positive pivot; the flag travels as a NaN in the
+    exchanged trial sum — or the ranks would disagree on `continual` and the next collective would never complete."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'mgf.pt')
+    mp.spawn(_mg_worker, args=(2, 29641 + len(name), out, 'nccl', name, True, dict(lm_max=-1.0)), nprocs=2, join=True)
+    steps = _MG_GRAPHS[name][1]
+    views = [torch.load(f'{out}.{r}') for r in range(2)]
+    assert views[0] == views[1]
+    assert views[0]['info'] == 1 and views[0]['steps'] == steps and views[0]['tries'] == steps
+    g = _MG_GRAPHS[name][0]()
+    assert np.array_equal(torch.load(out)['nodes'].numpy(), g.init_nodes)          # parameters untouched
 
 
 @pytest.mark.parametrize('world', [2, 4])
