@@ -180,6 +180,10 @@ int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream);
  * block) alone), which = 2: everything right of it.  After part 1 the next block can be factored and broadcast on a second
  * stream while part 2 of this block still runs (islam_b200/dist.py). */
 int islam_pvgo_root_update_part(islam_pvgo* h, int64_t k0, int32_t which, void* stream);
+/* optional, after try_mid: zero this rank's copy of the tile columns it does not own.  A factored block can then travel as
+ * all-reduce(SUM) of R[k0 * ld, ...) instead of a broadcast (the owner contributes the block, everybody else zeros): on
+ * NVSwitch the reduction + multicast happen in the fabric. */
+int islam_pvgo_root_zero_foreign(islam_pvgo* h, void* stream);
 int islam_pvgo_lm_try_mid2(islam_pvgo* h, void* stream);
 /* peer mailboxes: every rank exports the IPC handle of its mailbox (64 bytes), the caller all-gathers them (rank order)
  * and hands the table to every rank.  LM state info = 2 reports a peer that never answered (2 s timeout). */

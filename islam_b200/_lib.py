@@ -77,6 +77,7 @@ _SIGS = {
     'islam_pvgo_root_panel': (C.c_int, [_P, C.c_int64, _P]),
     'islam_pvgo_root_update': (C.c_int, [_P, C.c_int64, _P]),
     'islam_pvgo_root_update_part': (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
+    'islam_pvgo_root_zero_foreign': (C.c_int, [_P, _P]),
     'islam_pvgo_sums_buffer': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     'islam_pvgo_lm_try_end': (C.c_int, [_P, _P]),
     'islam_pvgo_var_parts': (C.c_int, [_P, _P]),

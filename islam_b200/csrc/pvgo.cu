@@ -1068,6 +1068,11 @@ extern "C" int islam_pvgo_root_update(islam_pvgo* h, int64_t k0, void* stream) {
     if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % SY_T) return -1;
     return launch_root_update(h, (cudaStream_t)stream, (int)k0, 0);
 }
+extern "C" int islam_pvgo_root_zero_foreign(islam_pvgo* h, void* stream) {
+    if (!h || !h->root_dist()) return -1;
+    k_root_zero_foreign<<<h->rv.n, 256, 0, (cudaStream_t)stream>>>(h->st.p, h->rv, h->opts.n_parts, h->opts.part);
+    return (int)cudaGetLastError();
+}
 extern "C" int islam_pvgo_root_update_part(islam_pvgo* h, int64_t k0, int32_t which, void* stream) {
     if (!h || !h->root_dist() || k0 < 0 || k0 >= h->rv.n || k0 % SY_T || which < 1 || which > 2) return -1;
     return launch_root_update(h, (cudaStream_t)stream, (int)k0, 0, which);

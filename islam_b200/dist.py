@@ -97,6 +97,8 @@ class ShardedPVGO:
             t.copy_(c)
 
     def _bcast(self, t, src):
+        if self.root_exchange == 'allreduce':   # owner's block + zeros everywhere else (islam_pvgo_root_zero_foreign)
+            return self._allreduce(t)
         if self._nccl:
             dist.broadcast(t, src, group=self.group)
         else:                                   # gloo: stage through the host
@@ -121,6 +123,8 @@ class ShardedPVGO:
             self._root_ev = [torch.cuda.Event() for _ in range(2)]
         side, side_p = self._side, C.c_void_p(self._side.cuda_stream)
         blocks = list(range(0, n, nb))
+        if self.root_exchange == 'allreduce':
+            _lib.check(L.islam_pvgo_root_zero_foreign(h, st), 'islam_pvgo_root_zero_foreign')
         _lib.check(L.islam_pvgo_root_panel(h, 0, st), 'islam_pvgo_root_panel')
         self._bcast(self.root_R[0:min(nb, n) * ld], self._root_src[0])
         for b, k0 in enumerate(blocks):
@@ -144,6 +148,9 @@ class ShardedPVGO:
 
     _side = None
     lookahead = os.environ.get('ISLAM_ROOT_LOOKAHEAD', '1') != '0'
+    # how a factored block reaches the other ranks: 'broadcast' (NCCL broadcast from the owner) or 'allreduce' (SUM of the
+    # owner's block and zeros: in-fabric reduction + multicast on NVSwitch)
+    root_exchange = os.environ.get('ISLAM_ROOT_EXCHANGE', 'broadcast')
 
     def lm_try(self):
         s = self.s
