@@ -12,9 +12,10 @@ timeout 200 python tools/level_timeline.py > gpurun_out/timeline.log 2>&1
 timeout 200 python tools/phase_clocks.py 1 4 64 256 512 > gpurun_out/phase.log 2>&1
 ISLAM_FRONT4=1 timeout 200 python tools/level_timeline.py > gpurun_out/timeline_front4.log 2>&1
 ISLAM_FRONT4=1 timeout 200 python tools/phase_clocks.py 64 > gpurun_out/phase_front4.log 2>&1
-ISLAM_FRONT4=1 timeout 300 python -m pytest tests/test_gpu_pvgo.py -m gpu -q > gpurun_out/t_front4.log 2>&1; echo "rc=$?" >> gpurun_out/t_front4.log
+ISLAM_FRONT4=1 timeout 200 python -m pytest tests/test_gpu_pvgo.py -m gpu -q -k "linearize or solve_matches or lm_steps or full_size" > gpurun_out/t_front4.log 2>&1; echo "rc=$?" >> gpurun_out/t_front4.log
 timeout 200 python tools/scale_bench.py > gpurun_out/scale_bench.log 2>&1
 timeout 600 python tools/configs_bench.py > gpurun_out/configs.log 2>&1
+timeout 200 python tools/c4_bench.py --tries 2 > gpurun_out/c4_1gpu.log 2>&1
 timeout 300 python tools/small_bench.py > gpurun_out/small_bench.log 2>&1
 ./tools/lat_bench > gpurun_out/lat_bench.log 2>&1
 ./tools/chain_bench > gpurun_out/chain_bench.log 2>&1
