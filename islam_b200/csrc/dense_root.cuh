@@ -2,11 +2,15 @@
 //
 // Loop-closure edges (|i-j| > band_max) make their endpoints the last poses to be eliminated (symbolic.cpp).  With a
 // handful of closures the root is an ordinary front; with thousands (BASELINE config 4: 2 000 closures => ~4 000 poses,
-// 36 000 unknowns) it is THE dense contraction of this path (north_star: "the dense Schur-complement GEMM where it
-// genuinely is a contraction").  It is stored as one column-major (n+1) x n panel — lower triangle plus the rhs row, like
-// every other front — and factored by a tiled right-looking float64 Cholesky: per 64-column block a single-CTA diagonal
-// factorisation, a row-parallel triangular solve of the panel below, and a 64x64-tiled SYRK/GEMM update of the trailing
-// matrix (the bulk: n^3/3 flops on the fp64 pipes of all 148 SMs).  The back-substitution walks the blocks in reverse.
+// 24 519 unknowns) it is THE dense contraction of this path (north_star: "the dense Schur-complement GEMM where it
+// genuinely is a contraction").  It is stored as one column-major panel — lower triangle plus the rhs row, like every
+// other front, leading dimension rounded to even — and factored by a blocked right-looking float64 Cholesky in 128-column
+// block steps: two 64-column panels (k_root_potrf: diagonal block AND its inverse; k_root_trsm: the panel below as a
+// tensor-core product with that inverse; a narrow update of the second panel in between), then ONE K = 128 update of the
+// trailing matrix (k_root_syrk: DMMA m8n8k4, operands staged by TMA bulk copies, two CTAs per SM) — the n^3/3 of the
+// work.  The back-substitution walks the blocks in reverse on all SMs (k_root_back).  Tiles sit on the absolute 128-grid of
+// the matrix, so a tile column has one owner for the whole factorisation: on several GPUs rank r factors / updates the
+// tile columns tc with tc % G == r and the factored blocks are broadcast (islam_b200/dist.py, include/islam_pvgo.h).
 // Only the tau / phi variables of a closure pose are promoted (symbolic3.cpp): 6 unknowns per pose, not 9.
 // Children scatter their update matrices with float64 atomics (the only non-deterministic summation order in the
 // library: a closure pose collects contributions from both chain neighbours and every closure it takes part in).

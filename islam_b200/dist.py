@@ -7,6 +7,10 @@ which every rank factors the few shared fronts redundantly and back-substitutes 
 rank needs for the common accept / roll-back decision (trial loss, quality term) do not go through a second collective:
 the kernel that closes the try stores them straight into the peers' mailboxes over NVLink (CUDA IPC peer memory) and
 sums the G messages in rank order (exchange='p2p', the default; exchange='nccl' keeps a 16-byte all-reduce instead).
+
+A DENSE loop-closure root (BASELINE config 4) is the one part with enough arithmetic to shard: it is assembled by an
+all-reduce of the ranks' shares and factored by all ranks together, 1-D block-column-cyclic, every factored 128-column
+block broadcast from its owner with one block of look-ahead on a high-priority stream (_root_factor).
 """
 import ctypes as C
 import os
