@@ -12,8 +12,9 @@
 // the matrix, so a tile column has one owner for the whole factorisation: on several GPUs rank r factors / updates the
 // tile columns tc with tc % G == r and the factored blocks are broadcast (islam_b200/dist.py, include/islam_pvgo.h).
 // Only the tau / phi variables of a closure pose are promoted (symbolic3.cpp): 6 unknowns per pose, not 9.
-// Children scatter their update matrices with float64 atomics (the only non-deterministic summation order in the
-// library: a closure pose collects contributions from both chain neighbours and every closure it takes part in).
+// Children that share a root variable are coloured on the host and extend-add colour by colour with plain additions: the
+// summation order is fixed, so the dense root is bitwise reproducible like the rest of the library (float64 atomics only
+// remain as the fall-back for more than 64 colours, and in k_root_orig, whose entries are written once).
 #pragma once
 #include "common.cuh"
 #include "solver3.cuh"
@@ -85,9 +86,10 @@ k_root_diag(const LMState* __restrict__ st, RootView rv, const double* __restric
 constexpr int ROOT_ALL_CHILDREN = -2;
 __global__ void __launch_bounds__(256)
 k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const double* __restrict__ Ubuf, int force,
-                int want_part) {
+                int want_part, int first, int atomic) {
+    // atomic == 0: the children of this launch are one colour class (pvgo.cu): no two of them touch the same root entry
     if (!force && !st->active) return;
-    const int k = rv.children[blockIdx.x];
+    const int k = rv.children[first + blockIdx.x];
     const int c = m.children[k];
     if (want_part != ROOT_ALL_CHILDREN && m.part[c] != want_part) return;
     const int* cm = m.cmap + m.cmap_off[k];
@@ -99,7 +101,8 @@ k_root_children(const LMState* __restrict__ st, RootView rv, Front3Meta m, const
         const double* col = U + f3_ucol(cc, ub);
         for (int r = cc + lane; r < ub; r += 32) {
             const int pr = (r == ub - 1) ? rv.n : 3 * cm[r / 3] + r % 3;
-            atomicAdd(&rv.R[pr + (size_t)pc * rv.ld], col[r]);
+            double* dst = &rv.R[pr + (size_t)pc * rv.ld];
+            if (atomic) atomicAdd(dst, col[r]); else *dst += col[r];
         }
     }
 }

@@ -205,6 +205,7 @@ struct islam_pvgo {
     bool p2p = false;
     RootView rv;
     bool has_root = false;
+    std::vector<int> root_colour_off;                // children of the dense root sorted by colour: [colour] -> first child; empty: atomics
     bool root_dist() const { return has_root && opts.n_parts > 1; }      // dense root factored block-column-cyclically over the ranks
     DevBuf<LMState> st;
     DevBuf<islam_lm_params> d_prm;
@@ -532,6 +533,38 @@ extern "C" int islam_pvgo_create(islam_pvgo** out, int32_t N, int32_t E, const i
         const int fr = q.dense_root, K = q.f_np[fr];
         std::vector<int> rvars(q.f_vars.begin() + q.f_vars_off[fr], q.f_vars.begin() + q.f_vars_off[fr] + K), kids;
         for (int k = q.f_child_off[fr]; k < q.f_child_off[fr + 1]; ++k) kids.push_back(k);
+        // Children that share a root variable would add into the same entries: colour them (greedy; the chain pieces between
+        // two fully promoted poses only share those poses, so two or three colours) and extend-add colour by colour with plain
+        // additions — fixed summation order, no atomics, bitwise reproducible like the rest of the library.
+        {
+            std::vector<unsigned long long> used(K, 0ULL);
+            std::vector<int> colour(kids.size(), 0);
+            int ncol = 0;
+            bool ok = true;
+            for (size_t c = 0; c < kids.size() && ok; ++c) {
+                const int k = kids[c];
+                unsigned long long m = 0ULL;
+                for (int t = q.c_map_off[k]; t < q.c_map_off[k + 1]; ++t) m |= used[q.c_map[t]];
+                int col = 0;
+                while (col < 64 && ((m >> col) & 1ULL)) ++col;
+                if (col >= 64) { ok = false; break; }
+                colour[c] = col;
+                ncol = std::max(ncol, col + 1);
+                for (int t = q.c_map_off[k]; t < q.c_map_off[k + 1]; ++t) used[q.c_map[t]] |= 1ULL << col;
+            }
+            h->root_colour_off.clear();
+            if (ok) {
+                std::vector<int> sorted;
+                sorted.reserve(kids.size());
+                for (int col = 0; col < ncol; ++col) {
+                    h->root_colour_off.push_back((int)sorted.size());
+                    for (size_t c = 0; c < kids.size(); ++c)
+                        if (colour[c] == col) sorted.push_back(kids[c]);
+                }
+                h->root_colour_off.push_back((int)sorted.size());
+                kids.swap(sorted);
+            }                                   // (> 64 colours: keep the atomics)
+        }
         cudaError_t e1 = h->d_root_vars.upload(rvars);
         if (e1 == cudaSuccess) e1 = h->d_root_children.upload(kids);
         if (e1 == cudaSuccess) e1 = h->root_x.alloc(2 * (3 * (size_t)K + 1));             // x and the running right-hand side t
@@ -789,6 +822,20 @@ static int launch_root_update(islam_pvgo* h, cudaStream_t s, int k0, int force, 
     return launch_root_syrk(h, s, k0, nk, k0 + nk, rv.n, force);
 }
 
+// extend-add of the root's children: colour by colour without atomics (or all at once with atomics when uncoloured)
+static void launch_root_children(islam_pvgo* h, cudaStream_t s, int force, int want_part) {
+    const RootView& rv = h->rv;
+    if (!rv.nchildren) return;
+    if (h->root_colour_off.empty()) {
+        k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, want_part, 0, 1);
+        return;
+    }
+    for (size_t c = 0; c + 1 < h->root_colour_off.size(); ++c) {
+        const int first = h->root_colour_off[c], cnt = h->root_colour_off[c + 1] - first;
+        if (cnt > 0) k_root_children<<<cnt, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, want_part, first, 0);
+    }
+}
+
 static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale) {
     if (!h->has_root) return 0;
     const RootView& rv = h->rv;
@@ -802,12 +849,12 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
         CK(cudaMemsetAsync(h->root_diag.p, 0, sizeof(double) * rv.n, s));
         k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min,
                                                         q.lm_max, h->root_diag.p);
-        if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, h->opts.part);
+        launch_root_children(h, s, force, h->opts.part);
         return (int)cudaGetLastError();
     }
     k_root_orig<<<(tasks + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->fm, h->Hd.p, h->Ho.p, h->g.p, h->d_prm.p, forced_scale, q.lm_min,
                                                     q.lm_max, (double*)nullptr);
-    if (rv.nchildren) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, force, ROOT_ALL_CHILDREN);
+    launch_root_children(h, s, force, ROOT_ALL_CHILDREN);
     for (int k0 = 0; k0 < rv.n; k0 += SY_T) {
         int rc = launch_root_panel(h, s, k0, force);
         if (!rc) rc = launch_root_update(h, s, k0, force);
@@ -820,7 +867,7 @@ static int launch_root_factor(islam_pvgo* h, cudaStream_t s, double forced_scale
 // factors those redundantly) and the clamped + damped diagonal
 static int launch_root_finish(islam_pvgo* h, cudaStream_t s) {
     const RootView& rv = h->rv;
-    if (rv.nchildren && h->n_shared > 0) k_root_children<<<rv.nchildren, 256, 0, s>>>(h->st.p, rv, h->fm, h->Ubuf.p, 0, -1);
+    if (h->n_shared > 0) launch_root_children(h, s, 0, -1);
     k_root_diag<<<(rv.n + 127) / 128, 128, 0, s>>>(h->st.p, rv, h->root_diag.p, h->d_prm.p);
     return (int)cudaGetLastError();
 }
