@@ -1,4 +1,6 @@
 """GPU parity tests (through the C ABI) of kernel families 1 and 2 and of the LM driver against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -394,6 +396,35 @@ def test_config4_large_dense_root_properties():
     # bitwise reproducible: the root's children extend-add colour by colour without atomics (csrc/pvgo.cu, dense_root.cuh)
     assert np.array_equal(out[0][1], out[1][1])
     assert out[0][0] == out[1][0]
+
+
+def test_config4_full_size_against_oracle_fixture():
+    """FULL BASELINE config 4 (50 000 poses, 51 999 edges, 2 000 loop closures => dense root of 24 519 unknowns) against the
+    float64 CPU oracle: loss and reject count after each of 8 LM steps, poses after step 3 (far from convergence: the iterates
+    themselves agree) and after step 8.  The oracle run (~80 s of CPU per step) is committed as a fixture,
+    tests/golden/make_c4_golden.py; poses are compared on every 25th pose after align_to."""
+    fx = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'c4_oracle_steps.npz'))
+    steps, stride, mid = int(fx['steps']), int(fx['stride']), int(fx['mid'])
+    g = synth.config4()
+    assert g.N == int(fx['N']) and g.E == int(fx['E'])
+    s = _solver(g)
+    s.lm_reset(radius=g.radius, max_steps=steps, use_scheduler=0)
+    # measured: losses agree to <= 1.2e-6 relative at every step; poses to 2.4e-5 relative (1.2 mm, 1.4e-5 rad) at steps 3 and 8.
+    # The problem is nowhere near a fixed point there (it creeps for > 60 steps under heavy damping), so the float32 state /
+    # linearisation (the reference's dtype) and the oracle's float64 iterates differ more than at convergence (C2: 6.7e-7).
+    errs, GATE_MID, GATE_END = {}, 5e-5, 5e-5
+    for k in range(steps):
+        st = s.lm_step()
+        assert st.info == 0 and st.reject_count == int(fx['rejects'][k])
+        assert abs(st.loss - fx['losses'][k]) <= 1e-5 * abs(fx['losses'][k]), (k, st.loss, fx['losses'][k])
+        if k + 1 in (mid, steps):
+            n, v = s.align(g.init_nodes[0])
+            rn, rv = (fx['nodes_mid'], fx['vels_mid']) if k + 1 == mid else (fx['nodes'], fx['vels'])
+            err = po.rel_pose_error(n.cpu().numpy()[::stride], rn)
+            errs[k + 1] = err
+            assert np.abs(v.cpu().numpy()[::stride] - rv).max() <= 1e-3
+    print('C4 full size, relative pose error vs the float64 oracle after step', errs)
+    assert errs[mid]['rel'] <= GATE_MID and errs[steps]['rel'] <= GATE_END, errs
 
 
 def test_rejected_tries_follow_the_oracle():
