@@ -226,7 +226,8 @@ def test_sharded_ranks_on_one_gpu(world, name, tmp_path):
     its panel broadcasts (csrc/dense_root.cuh, include/islam_pvgo.h) — run wherever the GPU tests run."""
     import torch.multiprocessing as mp
     out = str(tmp_path / 'mg1.pt')
-    mp.spawn(_mg_worker, args=(world, 29571 + world + len(name), out, 'nccl', name, True), nprocs=world, join=True)
+    port = 29571 + 10 * list(_MG_GRAPHS).index(name) + world          # one rendezvous port per case
+    mp.spawn(_mg_worker, args=(world, port, out, 'nccl', name, True), nprocs=world, join=True)
     r = _check_sharded(out, name, loss_rtol=1e-8)
     assert (r['root_n'] > 0) == (name == 'lcdense')
 
