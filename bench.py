@@ -405,7 +405,15 @@ def _other_configs(rank, world, dev, sh_cls):
     tm = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    out['C4_loop_closures'] = {'ms_per_lm_iteration': float(tm.item()) / max(1, st.tries_total - n0), 'n_gpus': world,
+    ms_it = float(tm.item()) / max(1, st.tries_total - n0)
+    n_root = int(s4.dims.max_cols)                        # the dense root is by far the widest front
+    peak = 63 * 2 * 148 * 1.965e9 / 1e12                  # DMMA: 63 FMA/clk/SM measured (tools/pipe_bench.cu) x 148 SMs x 1.965 GHz
+    tfl = (n_root ** 3 / 3) / (ms_it * 1e-3) / 1e12
+    out['C4_dense_root_roofline'] = {'bound': 'tensor (fp64 DMMA)', 'unknowns': n_root, 'flops_per_factorisation': n_root ** 3 / 3,
+                                     'achieved': tfl, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': tfl / (peak * world),
+                                     'note': 'n^3/3 over the WHOLE LM iteration (subtrees, assembly, exchange, back-substitution '
+                                             'included); peak = own DMMA micro-benchmark per GPU x n_gpus, MEASURED_PEAKS has no fp64 entry'}
+    out['C4_loop_closures'] = {'ms_per_lm_iteration': ms_it, 'n_gpus': world,
                                'poses': int(g4.N), 'loop_closures': 2000, 'fronts': int(s4.dims.F),
                                'loss_after': st.loss, 'info': st.info,
                                'how': 'dense root factored block-column-cyclically by all ranks, NCCL broadcast of each factored block'
